@@ -1,0 +1,204 @@
+"""TEST INFRASTRUCTURE — pins the oracle against the UNMODIFIED reference and writes golden fixtures.
+
+Run in the build container (needs /root/reference; does not exist on the GPU box):
+
+    python oracle/gen_golden.py            # writes tests/golden/*.npz, prints the oracle-vs-reference report
+
+For every case the reference's own code (`models/ssr.py::SSR_Speech.inference`, WM-Encodec
+`encode/decode/wmdecode`) is executed on CPU with a seeded synthetic checkpoint
+(`ssr_speech_b200.synth`), the oracle restatement is executed on the same inputs, the two are
+compared, and the reference's outputs are stored.  Fixtures hold inputs + reference outputs only
+(weights are regenerated from their seed by the tests).
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+import ref_loader  # noqa: E402
+from lm_oracle import LMOracle  # noqa: E402
+from codec_oracle import CodecOracle  # noqa: E402
+import ssr_speech_b200 as pkg  # noqa: E402
+from ssr_speech_b200 import seq as seqmod  # noqa: E402
+from ssr_speech_b200.config import CodecConfig, cfg_tiny  # noqa: E402
+from ssr_speech_b200.synth import calibrate_codebooks, make_codec_state_dict, make_lm_state_dict  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+LM_CASES = [
+    # name, Lx, T, mask_interval, decode kwargs, seed
+    dict(name="tts_greedy", Lx=7, T=20, spans=[[20, 20]], seed=11,
+         kw=dict(top_k=1, top_p=1.0, temperature=1.0, stop_repetition=-1, kvcache=1, cfg_coef=1.5, cfg_stride=1, aug_text=False)),
+    dict(name="edit_cfg_sampled", Lx=9, T=40, spans=[[12, 25]], seed=12,
+         kw=dict(top_k=0, top_p=0.8, temperature=1.0, stop_repetition=2, kvcache=1, cfg_coef=1.5, cfg_stride=2, aug_text=True)),
+    dict(name="edit2_cfg_greedy", Lx=8, T=36, spans=[[5, 9], [20, 28]], seed=13,
+         kw=dict(top_k=1, top_p=1.0, temperature=1.0, stop_repetition=-1, kvcache=1, cfg_coef=2.0, cfg_stride=3, aug_text=True)),
+    dict(name="tts_cfg_temp_topk", Lx=6, T=16, spans=[[16, 16]], seed=14,
+         kw=dict(top_k=20, top_p=0.9, temperature=0.7, stop_repetition=3, kvcache=1, cfg_coef=1.5, cfg_stride=1, aug_text=True)),
+    dict(name="edit_head_nokv", Lx=6, T=24, spans=[[0, 6]], seed=15,
+         kw=dict(top_k=1, top_p=1.0, temperature=1.0, stop_repetition=-1, kvcache=0, cfg_coef=1.5, cfg_stride=1, aug_text=False)),
+]
+SILENCE = [3, 17, 40]   # tiny-vocab stand-ins for the reference default [1388,1898,131]
+
+
+def run_lm_cases():
+    ssr = ref_loader.load_reference_ssr()
+    cfg = cfg_tiny()
+    sd = make_lm_state_dict(cfg, seed=7)
+    model = ssr.SSR_Speech(cfg.to_namespace()).eval()
+    missing = model.load_state_dict(sd, strict=True)
+    print("reference SSR_Speech loaded synthetic state_dict:", missing)
+    oracle = LMOracle(cfg, sd)
+    report = []
+    for case in LM_CASES:
+        g = torch.Generator().manual_seed(case["seed"])
+        Lx, T = case["Lx"], case["T"]
+        x = torch.randint(0, cfg.text_vocab_size, (1, Lx), generator=g)
+        y = torch.randint(0, cfg.audio_vocab_size, (1, T, cfg.n_codebooks), generator=g)
+        mi = torch.tensor([case["spans"]], dtype=torch.long)
+        kw = dict(case["kw"])
+        # ---- reference run (global CPU RNG seeded like inference_v2.seed_everything) -----------
+        torch.manual_seed(case["seed"])
+        with torch.no_grad():
+            res, marks, masks, nmi = model.inference(x, torch.tensor([Lx]), x, torch.tensor([Lx]), y, y,
+                                                     mask_interval=mi, silence_tokens=SILENCE, **kw)
+        # ---- oracle run with the same RNG stream ------------------------------------------------
+        prep = seqmod.prepare(cfg, y[0].T.numpy().copy(), case["spans"])
+        okw = {k: v for k, v in kw.items() if k != "kvcache"}
+        torch.manual_seed(case["seed"])
+        spans = oracle.inference(x[0], torch.from_numpy(prep.prompt_tokens), prep.num_spans,
+                                 silence_tokens=SILENCE, incremental=bool(kw["kvcache"]), **okw)
+        ores, omarks, omasks, onmi = seqmod.finalize(cfg, prep, spans)
+        same = (ores.shape == tuple(res[0].shape) and np.array_equal(ores, res[0].numpy())
+                and np.array_equal(omarks, marks[0].numpy()) and omasks == [tuple(m) for m in masks]
+                and onmi == [tuple(m) for m in nmi])
+        # ---- the same run again through explicit exponential noise (what the GPU path consumes) --
+        torch.manual_seed(case["seed"])
+        uncond = torch.randint(0, cfg.n_text_tokens, (1, Lx))[0] if kw["aug_text"] else None
+        n_steps = sum(len(s) for s in spans)
+        noise = torch.stack([torch.empty(cfg.n_codebooks, cfg.n_audio_tokens).exponential_(1) for _ in range(n_steps)])
+        trace = []
+        spans2 = oracle.inference(x[0], torch.from_numpy(prep.prompt_tokens), prep.num_spans, silence_tokens=SILENCE,
+                                  uncond_x=uncond, noise=noise, trace=trace, **okw)
+        same_noise = all(np.array_equal(a, b) for a, b in zip(spans, spans2))
+        report.append((case["name"], same, same_noise, tuple(res.shape)))
+        print(f"[lm] {case['name']:<20} oracle==reference: {same}   noise-path==multinomial-path: {same_noise}   res {tuple(res.shape)}")
+        np.savez_compressed(
+            os.path.join(GOLD, f"lm_{case['name']}.npz"),
+            x=x[0].numpy(), y=y[0].numpy(), mask_interval=np.asarray(case["spans"]), silence=np.asarray(SILENCE),
+            kw=json.dumps(kw), seed=case["seed"], weights_seed=7,
+            uncond_x=(uncond.numpy() if uncond is not None else np.zeros(0, np.int64)),
+            noise=noise.numpy().astype(np.float32),
+            ref_res=res[0].numpy(), ref_marks=marks[0].numpy(), ref_masks=np.asarray(masks), ref_nmi=np.asarray(nmi),
+            ref_span_lens=np.asarray([len(s) for s in spans]),
+            ref_span_tokens=np.concatenate(spans, 0),
+            raw_logits_step0=trace[0].raw_logits.numpy(), probs_step0=trace[0].probs.numpy(),
+            raw_logits_last=trace[-1].raw_logits.numpy(),
+        )
+    # teacher-forced logits fixture straight from the reference modules (no loop)
+    g = torch.Generator().manual_seed(99)
+    x = torch.randint(0, cfg.text_vocab_size, (11,), generator=g)
+    toks = torch.randint(0, cfg.audio_vocab_size, (cfg.n_codebooks, 30), generator=g)
+    with torch.no_grad():
+        xi = model.text_positional_embedding(model.text_embedding(x[None]))
+        yi = model.audio_positional_embedding(model.embed_y(toks[:, :, None]))
+        S = xi.shape[1] + yi.shape[1]
+        mask = torch.triu(torch.ones(S, S), diagonal=1).bool()
+        out, _ = model.decoder((torch.cat([xi, yi], 1), None), mask=mask)
+        h = out[:, xi.shape[1]:]
+        ref_logits = torch.stack([model.predict_layer[k](h) for k in range(cfg.n_codebooks)], 2)[0]  # [T,K,V]
+    ol = oracle.teacher_forced_logits(x, toks)
+    err = (ol - ref_logits).abs().max().item()
+    print(f"[lm] teacher-forced logits oracle vs reference max-abs err {err:.3e}")
+    np.savez_compressed(os.path.join(GOLD, "lm_teacher_forced.npz"), x=x.numpy(), toks=toks.numpy(),
+                        ref_logits=ref_logits.numpy(), weights_seed=7)
+    return report, err
+
+
+def run_codec_cases():
+    cfg = CodecConfig()
+    model = ref_loader.build_reference_codec()
+    # calibration pass: per-stage residual statistics for the codebook recipe (synth.make_codebook)
+    sd = make_codec_state_dict(cfg, seed=3)
+    model.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(1234)
+    t = torch.arange(6400) / 16000.0
+    wav = torch.stack([0.1 * torch.randn(6400, generator=g) * (0.3 + torch.sin(2 * np.pi * (3 + 2 * i) * t) ** 2)
+                       + 0.05 * torch.sin(2 * np.pi * (200 + 150 * i) * t) for i in range(2)])[:, None]
+    wav[1, :, 4000:] *= 0.2
+    tc = torch.arange(32000) / 16000.0
+    cal = torch.stack([0.1 * torch.randn(32000, generator=g) * (0.3 + torch.sin(2 * np.pi * (1 + i) * tc) ** 2)
+                       + 0.05 * torch.sin(2 * np.pi * (200 + 150 * i) * tc) for i in range(4)])[:, None]
+    with torch.no_grad():
+        emb = model.encoder(cal)
+    mu, sigma = calibrate_codebooks(cfg, 3, emb.permute(0, 2, 1).reshape(-1, cfg.dimension))
+    sd = make_codec_state_dict(cfg, seed=3, codebook_mu=mu, codebook_sigma=sigma)
+    model.load_state_dict(sd, strict=True)
+    oracle = CodecOracle(cfg, sd)
+    with torch.no_grad():
+        codes, scale, emb = model.encode(wav)
+        dec = model.decode(codes, None)
+        marks = torch.zeros(2, codes.shape[-1], dtype=torch.long)
+        marks[0, 5:12] = 1
+        marks[1, 0:4] = 1
+        wm, mlog = model.wmdecode(codes, marks, wav, None)
+    ocodes, _, oemb = oracle.encode(wav)
+    odec = oracle.decode(codes)
+    owm, omlog = oracle.wmdecode(codes, marks, wav)
+    rep = dict(
+        emb_err=(oemb - emb).abs().max().item(), emb_max=emb.abs().max().item(),
+        codes_equal=bool(torch.equal(ocodes, codes)), n_distinct=[int(codes[:, q].unique().numel()) for q in range(cfg.n_q)],
+        codes_given_ref_emb=bool(torch.equal(oracle.rvq_encode(emb), codes)),
+        dec_err=(odec - dec).abs().max().item(), dec_max=dec.abs().max().item(),
+        wm_err=(owm - wm).abs().max().item(), wm_max=wm.abs().max().item(),
+        mlog_err=(omlog - mlog).abs().max().item(),
+    )
+    print("[codec] oracle vs reference:", json.dumps(rep))
+    np.savez_compressed(os.path.join(GOLD, "codec_small.npz"), wav=wav.numpy(), weights_seed=3,
+                        codebook_mu=mu.numpy(), codebook_sigma=sigma.numpy(), ref_emb=emb.numpy(), ref_codes=codes.numpy(),
+                        ref_dec=dec.numpy(), marks=marks.numpy(), ref_wm=wm.numpy(), ref_mark_logits=mlog.numpy())
+    # config 1 of BASELINE.json: demo wav round trip (first 2 s stored; full-length checked here only)
+    try:
+        from scipy.io import wavfile
+        sr, data = wavfile.read(os.path.join(ref_loader.REF_ROOT, "demo", "84_121550_000074_000000.wav"))
+        data = torch.from_numpy(np.asarray(data, dtype=np.float32))[None, None]
+        pad = (320 - data.shape[-1] % 320) % 320          # data/tokenizer.py:148-151
+        data = torch.nn.functional.pad(data, (0, pad))
+        with torch.no_grad():
+            c_full, _, e_full = model.encode(data)
+            d_full = model.decode(c_full, None)
+        oc, _, oe = oracle.encode(data)
+        od = oracle.decode(c_full)
+        print(f"[codec] demo wav sr={sr} len={data.shape[-1]} frames={c_full.shape[-1]} "
+              f"codes_equal={bool(torch.equal(oc, c_full))} emb_err={(oe - e_full).abs().max().item():.3e} "
+              f"dec_err={(od - d_full).abs().max().item():.3e}")
+        n = 32000
+        seg = data[..., :n]
+        with torch.no_grad():
+            c_seg, _, e_seg = model.encode(seg)
+            d_seg = model.decode(c_seg, None)
+        np.savez_compressed(os.path.join(GOLD, "codec_demo2s.npz"), wav=seg.numpy(), weights_seed=3,
+                            codebook_mu=mu.numpy(), codebook_sigma=sigma.numpy(), ref_emb=e_seg.numpy(), ref_codes=c_seg.numpy(),
+                            ref_dec=d_seg.numpy(), full_len=data.shape[-1], full_frames=c_full.shape[-1])
+    except Exception as e:  # pragma: no cover
+        print("[codec] demo wav case skipped:", repr(e))
+    return rep
+
+
+if __name__ == "__main__":
+    os.makedirs(GOLD, exist_ok=True)
+    torch.set_num_threads(8)
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which in ("all", "lm"):
+        run_lm_cases()
+    if which in ("all", "codec"):
+        run_codec_cases()
