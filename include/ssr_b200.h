@@ -1,0 +1,180 @@
+/* ssr_b200.h — C ABI of libssr_b200.so: the B200 (sm_100a) implementation of SSR-Speech's inference
+ * hot path.  Plain C types only; no torch types, no exceptions, no ownership transfer of caller memory.
+ *
+ * The reference (WangHelin1997/SSR-Speech) is 100 % Python/PyTorch and has NO FFI/plugin interface
+ * (SURVEY.md §0 #10, §8b); the drop-in boundary is therefore Python-level and this library is bound by
+ * the thin ctypes layer in ssr-speech_b200/_lib.py.  Each entry point cites the reference interface it
+ * replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; ssrb_last_error() returns the message
+ *     of the last failure on the calling thread's context (static storage, do not free).
+ *   - "dev" pointers are device pointers on the context's device, "host" pointers are host memory.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  All work is enqueued
+ *     asynchronously on it unless the function is documented as synchronising.
+ *   - a context is bound to one device and is not thread-safe.
+ */
+#ifndef SSR_B200_H
+#define SSR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSRB_DTYPE_F32  0
+#define SSRB_DTYPE_BF16 1
+
+#define SSRB_MAX_SPANS     3
+#define SSRB_MAX_SILENCE   8
+
+const char* ssrb_last_error(void);
+int ssrb_version(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches claim) */
+uint64_t ssrb_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Autoregressive LM  —  replaces models/ssr.py::SSR_Speech (inference path) and the modules under it
+ * (models/modules/transformer.py, activation.py, embedding.py).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct ssrb_lm ssrb_lm;
+
+typedef struct {
+    /* model (the fields SSR_Speech.__init__ reads from ckpt["config"], models/ssr.py:113-179) */
+    int d_model, n_head, n_layer, ffn_dim;
+    int n_codebooks, n_audio_tokens, n_text_tokens, head_hidden;
+    int empty_token, eog, eos, sos, mts, max_n_spans;
+    /* engine capacity */
+    int max_rows;            /* transformer rows resident at once = utterances x (2 if CFG else 1)   */
+    int max_seq;             /* max cached positions per row (text + audio)                           */
+    int max_prefill_tokens;  /* packed prompt positions processed per prefill chunk                   */
+    int max_steps;           /* max decode iterations recorded per utterance                          */
+    int weight_dtype;        /* SSRB_DTYPE_F32: fp32 weights/KV/activations (parity mode)
+                                SSRB_DTYPE_BF16: bf16 weights/KV/GEMM operands, fp32 accumulate (production) */
+    int gemm_impl;           /* 0 = auto, 1 = SIMT kernels only, 2 = tcgen05 kernels (bf16 only)      */
+} ssrb_lm_config;
+
+/* SSR_Speech(config) + .to(device)                                        — models/ssr.py:104-179 */
+int ssrb_lm_create(const ssrb_lm_config* cfg, int device, ssrb_lm** out);
+void ssrb_lm_destroy(ssrb_lm* lm);
+
+/* load_state_dict(ckpt["model"]) — one call per state_dict entry, `name` is the reference key
+ * (inference_v2.py:198-202).  `host` is fp32, row-major, `shape[ndim]`.
+ * The extra key "pe_table" [n_pos, d_model] carries the sinusoid table of
+ * models/modules/embedding.py:69-92 (computed by the caller so it matches the reference bit for bit).
+ * Synchronises. */
+int ssrb_lm_load_tensor(ssrb_lm* lm, const char* name, const float* host, const int64_t* shape, int ndim);
+/* returns 0 when every tensor the engine needs has been loaded, else 1 (message lists missing keys) */
+int ssrb_lm_check_loaded(ssrb_lm* lm);
+
+/* sampling / CFG arguments of SSR_Speech.inference                       — models/ssr.py:504-524 */
+typedef struct {
+    int   top_k;             /* <=0: disabled                                  (ssr.py:38-45)          */
+    float top_p;             /* >=1: disabled                                  (ssr.py:47-67)          */
+    float temperature;       /*                                                (ssr.py:80-81)          */
+    int   stop_repetition;   /* <=0: disabled                                  (ssr.py:725-730)        */
+    int   n_silence;
+    int   silence_tokens[SSRB_MAX_SILENCE];
+    float cfg_coef;          /*                                                (ssr.py:691-696)        */
+    int   cfg_stride;
+    int   aug_text;          /* 1: every utterance owns 2 rows (cond, uncond)  (ssr.py:571-577)        */
+    uint64_t seed;           /* counter-based RNG seed when `noise` is NULL                            */
+} ssrb_sampling;
+
+/* one batch of utterances, host memory, all int32 */
+typedef struct {
+    int n_utt;
+    const int32_t* text;        /* [n_rows, text_stride] phoneme ids per ROW (row = utt*rpu + j)      */
+    int            text_stride;
+    const int32_t* text_len;    /* [n_utt]  (cond and uncond rows share the length, ssr.py:574)       */
+    const int32_t* prompt;      /* [n_utt, n_codebooks, prompt_stride] audio tokens before the first
+                                   generation slot = seq.prepare().prompt_tokens (ssr.py:604-626)     */
+    int            prompt_stride;
+    const int32_t* prompt_len;  /* [n_utt]                                                            */
+    const int32_t* n_spans;     /* [n_utt] number of masked spans to generate, 1..max_n_spans         */
+} ssrb_lm_batch;
+
+/* Prologue + first dec_forward of SSR_Speech.inference (ssr.py:596-689): embeds text/audio prompt,
+ * runs the prompt through the decoder (filling the in-place KV cache), samples iteration 1.
+ * `noise_dev`: optional device fp32 [max_steps, n_utt, n_codebooks, n_audio_tokens] Exp(1) variates
+ * consumed as sample = argmax(p / noise) — the identity torch.multinomial(num_samples=1) uses — so a
+ * caller can reproduce the reference's sampled tokens exactly; NULL = in-kernel Philox.  Asynchronous. */
+int ssrb_lm_begin(ssrb_lm* lm, const ssrb_lm_batch* batch, const ssrb_sampling* sp,
+                  const float* noise_dev, void* stream);
+
+/* Runs up to `n_steps` iterations of the `while True` loop (ssr.py:671-771) for all unfinished
+ * utterances without host synchronisation (CUDA-graph replay).  Asynchronous. */
+int ssrb_lm_decode(ssrb_lm* lm, int n_steps, void* stream);
+
+/* Synchronises `stream`, returns how many utterances have finished all their spans and the number of
+ * loop iterations executed so far (1 = only the prefill sample). */
+int ssrb_lm_poll(ssrb_lm* lm, void* stream, int* n_done, int* n_iter);
+
+/* Sampled tokens of utterance `utt`: out[n, n_codebooks] int32 for n = 0..*n_tokens-1 (every iteration
+ * of every span, including each span's EOG tail, concatenated); span_len[max_n_spans] = iterations per
+ * span.  Capacity `cap` iterations.  Synchronises. */
+int ssrb_lm_read_tokens(ssrb_lm* lm, void* stream, int utt, int32_t* out, int cap, int* n_tokens, int32_t* span_len);
+
+/* Test hook: raw head outputs of the most recent iteration, fp32 [n_rows, n_codebooks, n_audio_tokens]
+ * (the tensor `logits` of ssr.py:688 before CFG / rules).  Synchronises. */
+int ssrb_lm_read_logits(ssrb_lm* lm, void* stream, float* host_out);
+
+/* Test hook (teacher forcing; incremental == full-forward check of SURVEY §4): text[Lx], audio tokens
+ * [n_codebooks, Ty]; writes fp32 logits [Ty, n_codebooks, n_audio_tokens] for every audio position,
+ * computed by the prefill path.  Synchronises. */
+int ssrb_lm_teacher_forced(ssrb_lm* lm, const int32_t* text, int Lx, const int32_t* audio, int Ty,
+                           float* host_logits, void* stream);
+
+/* algorithmic HBM bytes of one decode iteration for the current batch state:
+ * weights streamed once + KV read for every active row + KV written.  Synchronises. */
+int ssrb_lm_step_bytes(ssrb_lm* lm, void* stream, double* weight_bytes, double* kv_bytes);
+
+/* ------------------------------------------------------------------------------------------------
+ * WM-Encodec  —  replaces audiocraft/models/wmencodec.py::WMEncodecModel.{encode,decode,wmdecode}
+ * and below it audiocraft/modules/{seanet,conv,lstm}.py, audiocraft/quantization/{vq,core_vq}.py.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct ssrb_codec ssrb_codec;
+
+typedef struct {
+    int channels, dimension, n_filters;
+    int n_ratios; int ratios[8];          /* decoder order, e.g. 8,5,4,2 (encoder reverses them)       */
+    int kernel_size, residual_kernel_size, last_kernel_size, compress, lstm_layers;
+    int n_q, bins;
+    int max_batch_chunk;                  /* utterances processed per internal pass (bounds workspace) */
+} ssrb_codec_config;
+
+int ssrb_codec_create(const ssrb_codec_config* cfg, int device, ssrb_codec** out);
+void ssrb_codec_destroy(ssrb_codec* c);
+
+/* load_state_dict(state['best_state']['model']) — `name` is the reference key (SURVEY Appendix D;
+ * audiocraft/solvers/wmcompression.py:302-312).  weight_g/weight_v pairs are folded (w = g*v/||v||)
+ * when both halves have arrived.  Synchronises. */
+int ssrb_codec_load_tensor(ssrb_codec* c, const char* name, const float* host, const int64_t* shape, int ndim);
+int ssrb_codec_check_loaded(ssrb_codec* c);
+
+/* WMEncodecModel.encode (wmencodec.py:324-339): wav_dev fp32 [B,1,T] (T multiple of hop) ->
+ * codes_dev int64 [B,n_q,T/hop], emb_dev fp32 [B,dimension,T/hop] (may be NULL). */
+int ssrb_codec_encode(ssrb_codec* c, const float* wav_dev, int B, int T, int64_t* codes_dev, float* emb_dev, void* stream);
+/* RVQ only: EuclideanCodebook.quantize on given latents (core_vq.py:164-172, :382-392) */
+int ssrb_codec_quantize(ssrb_codec* c, const float* emb_dev, int B, int Tf, int64_t* codes_dev, void* stream);
+/* WMEncodecModel.decode (wmencodec.py:341-356): codes int64 [B,n_q,Tf] -> wav fp32 [B,1,Tf*hop] */
+int ssrb_codec_decode(ssrb_codec* c, const int64_t* codes_dev, int B, int Tf, float* wav_dev, void* stream);
+/* WMEncodecModel.wmdecode (wmencodec.py:358-375; WMSEANetDecoder.forward seanet.py:555-600):
+ * marks int64 [B,Tf], wav_in fp32 [B,1,Tf*hop] -> wav_out fp32 [B,1,Tf*hop];
+ * mark_logits_dev fp32 [B,Tf,2] or NULL (the reference caller discards it, data/tokenizer.py:133). */
+int ssrb_codec_wmdecode(ssrb_codec* c, const int64_t* codes_dev, const int64_t* marks_dev, const float* wav_in_dev,
+                        int B, int Tf, float* wav_out_dev, float* mark_logits_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stand-alone op hooks used by the unit tests (each runs exactly the kernel the engines use).
+ * ---------------------------------------------------------------------------------------------- */
+/* C[M,N] = act(A[M,K] . W[N,K]^T + bias) (+ residual); dtype of A/W = `dtype`, C fp32.
+ * impl: 1 = SIMT, 2 = tcgen05 (bf16 only).  act: 0 none, 1 relu, 2 gelu(erf). */
+int ssrb_op_gemm(const void* A_dev, const void* W_dev, const float* bias_dev, const float* residual_dev,
+                 float* C_dev, int M, int N, int K, int dtype, int act, int impl, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSR_B200_H */

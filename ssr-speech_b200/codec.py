@@ -1,0 +1,264 @@
+"""WM-Encodec on the B200: `WMEncodecModel`, `AudioTokenizer`, `tokenize_audio`.
+
+Mirrors the reference's audio-side API for the inference path:
+  * audiocraft/models/wmencodec.py::WMEncodecModel.{encode, decode, wmdecode, decode_latent}  (:324-386)
+  * data/tokenizer.py::AudioTokenizer (:99-138) and tokenize_audio (:141-159)
+  * checkpoint layout of audiocraft/solvers/wmcompression.py::model_from_checkpoint (:281-315):
+    ``{'xp.cfg': cfg, 'best_state': {'model': state_dict}}``.
+All conv / LSTM / RVQ arithmetic runs in libssr_b200.so (fp32, sm_100a); there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+from .config import CodecConfig
+
+
+class WMEncodecModel:
+    def __init__(self, cfg: CodecConfig = CodecConfig(), max_batch_chunk: int = 8):
+        self.cfg = cfg
+        self.sample_rate = cfg.sample_rate
+        self.channels = cfg.channels
+        self.frame_rate = cfg.frame_rate
+        self.max_batch_chunk = max_batch_chunk
+        self._sd = None
+        self._device: Optional[torch.device] = None
+        self._h = None
+
+    # nn.Module-like surface
+    def load_state_dict(self, state_dict, strict: bool = True):
+        self._sd = {k: v.detach().to("cpu").contiguous() for k, v in state_dict.items() if torch.is_tensor(v)}
+        if strict and "encoder.model.0.conv.conv.bias" not in self._sd:
+            raise RuntimeError("Missing key(s) in state_dict: encoder.model.0.conv.conv.bias ...")
+        self._destroy()
+        return torch.nn.modules.module._IncompatibleKeys([], [])
+
+    def state_dict(self):
+        return dict(self._sd or {})
+
+    def eval(self):
+        return self
+
+    def to(self, device):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("ssr_speech_b200 codec runs on CUDA devices only (no CPU fallback)")
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        if device != self._device:
+            self._destroy()
+        self._device = device
+        return self
+
+    def _destroy(self):
+        if self._h is not None:
+            _lib.load().ssrb_codec_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self._destroy()
+        except Exception:
+            pass
+
+    def _engine(self):
+        if self._h is not None:
+            return self._h
+        if self._sd is None:
+            raise RuntimeError("load_state_dict must be called first")
+        if self._device is None:
+            self.to("cuda")
+        c = self.cfg
+        ratios = (C.c_int * 8)(*(list(c.ratios) + [0] * (8 - len(c.ratios))))
+        conf = _lib.CodecConfigC(channels=c.channels, dimension=c.dimension, n_filters=c.n_filters, n_ratios=len(c.ratios),
+                                 ratios=ratios, kernel_size=c.kernel_size, residual_kernel_size=c.residual_kernel_size,
+                                 last_kernel_size=c.last_kernel_size, compress=c.compress, lstm_layers=c.lstm, n_q=c.n_q,
+                                 bins=c.bins, max_batch_chunk=self.max_batch_chunk)
+        lib = _lib.load()
+        h = C.c_void_p()
+        with torch.cuda.device(self._device):
+            _lib.check(lib.ssrb_codec_create(C.byref(conf), self._device.index, C.byref(h)), "ssrb_codec_create")
+            self._h = h
+            fsd = {k: v for k, v in self._sd.items() if v.is_floating_point()}
+            _lib.load_state_dict_into(lib.ssrb_codec_load_tensor, h, fsd)
+            _lib.check(lib.ssrb_codec_check_loaded(h), "ssrb_codec_check_loaded")
+        return self._h
+
+    # ---- reference API -----------------------------------------------------------------------------------
+    @torch.no_grad()
+    def encode(self, x: torch.Tensor) -> Tuple[torch.Tensor, Optional[torch.Tensor], torch.Tensor]:
+        """x [B,1,T] float -> (codes [B,K,T/hop] int64, scale None (renormalize=False), emb [B,D,T/hop])."""
+        assert x.dim() == 3
+        h = self._engine()
+        x = x.to(self._device, torch.float32).contiguous()
+        B, Cc, T = x.shape
+        assert Cc == self.cfg.channels
+        Tf = T // self.cfg.hop_length
+        codes = torch.empty(B, self.cfg.n_q, Tf, dtype=torch.int64, device=self._device)
+        emb = torch.empty(B, self.cfg.dimension, Tf, dtype=torch.float32, device=self._device)
+        with torch.cuda.device(self._device):
+            _lib.check(_lib.load().ssrb_codec_encode(h, C.c_void_p(x.data_ptr()), B, T, C.c_void_p(codes.data_ptr()),
+                                                     C.c_void_p(emb.data_ptr()), _lib.stream_ptr()), "codec_encode")
+        return codes, None, emb
+
+    @torch.no_grad()
+    def quantize(self, emb: torch.Tensor) -> torch.Tensor:
+        """RVQ encode of given latents [B,D,Tf] -> codes [B,K,Tf] (quantization/core_vq.py:382-392)."""
+        h = self._engine()
+        emb = emb.to(self._device, torch.float32).contiguous()
+        B, D, Tf = emb.shape
+        codes = torch.empty(B, self.cfg.n_q, Tf, dtype=torch.int64, device=self._device)
+        with torch.cuda.device(self._device):
+            _lib.check(_lib.load().ssrb_codec_quantize(h, C.c_void_p(emb.data_ptr()), B, Tf, C.c_void_p(codes.data_ptr()),
+                                                       _lib.stream_ptr()), "codec_quantize")
+        return codes
+
+    @torch.no_grad()
+    def decode(self, codes: torch.Tensor, scale: Optional[torch.Tensor] = None) -> torch.Tensor:
+        assert scale is None, "renormalize=False for the SSR-Speech codec (encodec_audiogen_16khz.yaml:9-10)"
+        h = self._engine()
+        codes = codes.to(self._device, torch.int64).contiguous()
+        B, K, Tf = codes.shape
+        wav = torch.empty(B, 1, Tf * self.cfg.hop_length, dtype=torch.float32, device=self._device)
+        with torch.cuda.device(self._device):
+            _lib.check(_lib.load().ssrb_codec_decode(h, C.c_void_p(codes.data_ptr()), B, Tf, C.c_void_p(wav.data_ptr()),
+                                                     _lib.stream_ptr()), "codec_decode")
+        return wav
+
+    @torch.no_grad()
+    def wmdecode(self, codes: torch.Tensor, labels: torch.Tensor, wavform: torch.Tensor,
+                 scale: Optional[torch.Tensor] = None, return_marks: bool = True):
+        assert scale is None
+        h = self._engine()
+        codes = codes.to(self._device, torch.int64).contiguous()
+        labels = labels.to(self._device, torch.int64).contiguous()
+        wavform = wavform.to(self._device, torch.float32).contiguous()
+        B, K, Tf = codes.shape
+        T = Tf * self.cfg.hop_length
+        assert labels.shape == (B, Tf), labels.shape
+        assert wavform.shape == (B, 1, T), wavform.shape
+        out = torch.empty(B, 1, T, dtype=torch.float32, device=self._device)
+        marks = torch.empty(B, Tf, 2, dtype=torch.float32, device=self._device) if return_marks else None
+        with torch.cuda.device(self._device):
+            _lib.check(_lib.load().ssrb_codec_wmdecode(
+                h, C.c_void_p(codes.data_ptr()), C.c_void_p(labels.data_ptr()), C.c_void_p(wavform.data_ptr()), B, Tf,
+                C.c_void_p(out.data_ptr()), C.c_void_p(marks.data_ptr()) if marks is not None else None,
+                _lib.stream_ptr()), "codec_wmdecode")
+        return out, marks
+
+
+def _cfg_from_xp(xp_cfg) -> CodecConfig:
+    """Best-effort read of the resolved Hydra cfg stored in the checkpoint (wmcompression.py:302-304)."""
+    def get(o, k, d=None):
+        try:
+            return o[k] if k in o else d
+        except Exception:
+            return getattr(o, k, d)
+    cfg = CodecConfig()
+    try:
+        se, rv = get(xp_cfg, "seanet", {}), get(xp_cfg, "rvq", {})
+        cfg = CodecConfig(
+            channels=int(get(xp_cfg, "channels", 1)), dimension=int(get(se, "dimension", 128)),
+            n_filters=int(get(se, "n_filters", 64)), ratios=tuple(int(r) for r in get(se, "ratios", (8, 5, 4, 2))),
+            kernel_size=int(get(se, "kernel_size", 7)), residual_kernel_size=int(get(se, "residual_kernel_size", 3)),
+            last_kernel_size=int(get(se, "last_kernel_size", 7)), compress=int(get(se, "compress", 2)),
+            lstm=int(get(se, "lstm", 2)), n_q=int(get(rv, "n_q", 4)), bins=int(get(rv, "bins", 2048)),
+            sample_rate=int(get(xp_cfg, "sample_rate", 16000)))
+    except Exception:
+        pass
+    return cfg
+
+
+class AudioTokenizer:
+    """EnCodec audio tokenizer — same surface as reference data/tokenizer.py:99-138."""
+
+    def __init__(self, device: Any = None, signature=None, model: Optional[WMEncodecModel] = None):
+        if model is None:
+            state = torch.load(signature, map_location="cpu", weights_only=False)
+            assert state is not None and "xp.cfg" in state, f"Could not load compression model from ckpt: {signature}"
+            assert "best_state" in state and state["best_state"] != {}
+            model = WMEncodecModel(_cfg_from_xp(state["xp.cfg"]))
+            model.load_state_dict(state["best_state"]["model"])
+        self.sample_rate = model.sample_rate
+        self.channels = model.channels
+        if not device:
+            if not torch.cuda.is_available():
+                raise RuntimeError("ssr_speech_b200 needs a CUDA device (no CPU fallback)")
+            device = torch.device("cuda:0")
+        self._device = torch.device(device)
+        self.codec = model.to(self._device)
+
+    @property
+    def device(self):
+        return self._device
+
+    def encode(self, wav: torch.Tensor):
+        return self.codec.encode(wav.to(self.device))
+
+    def decode(self, frames: torch.Tensor, scale: Optional[torch.Tensor] = None) -> torch.Tensor:
+        return self.codec.decode(frames, scale)
+
+    def wmdecode(self, frames: torch.Tensor, marks: torch.Tensor, wav: torch.Tensor, scale: Optional[torch.Tensor] = None):
+        out, _ = self.codec.wmdecode(frames.to(self.device), marks.to(self.device), wav.to(self.device), scale,
+                                     return_marks=False)
+        return out
+
+
+def load_wav(path: str, offset: int = -1, num_frames: int = -1):
+    """torchaudio.load replacement (torchaudio's backends are absent in this image): float32 [C, T], sr."""
+    try:
+        import torchaudio
+        if offset != -1 and num_frames != -1:
+            return torchaudio.load(path, frame_offset=offset, num_frames=num_frames)
+        return torchaudio.load(path)
+    except Exception:
+        from scipy.io import wavfile
+        import numpy as np
+        sr, data = wavfile.read(path)
+        if data.dtype == np.int16:
+            data = data.astype(np.float32) / 32768.0
+        elif data.dtype == np.int32:
+            data = data.astype(np.float32) / 2147483648.0
+        data = torch.from_numpy(np.asarray(data, dtype=np.float32))
+        data = data[None] if data.ndim == 1 else data.T
+        if offset != -1 and num_frames != -1:
+            data = data[:, offset:offset + num_frames]
+        return data.contiguous(), sr
+
+
+def pad_to_multiple(wav: torch.Tensor, multiple: int = 320) -> torch.Tensor:
+    """data/tokenizer.py:148-151."""
+    pad = (multiple - (wav.shape[-1] % multiple)) % multiple
+    return F.pad(wav, (0, pad), "constant", 0) if pad > 0 else wav
+
+
+def convert_audio(wav: torch.Tensor, sr: int, target_sr: int, target_channels: int) -> torch.Tensor:
+    """data/tokenizer.py:87-97 (resampling is a no-op at 16 kHz; other rates need torchaudio)."""
+    assert wav.shape[0] in [1, 2], "Audio must be mono or stereo."
+    if target_channels == 1:
+        wav = wav.mean(0, keepdim=True)
+    elif target_channels == 2:
+        wav = wav.expand(target_channels, wav.shape[-1])
+    if sr != target_sr:
+        import torchaudio
+        wav = torchaudio.transforms.Resample(sr, target_sr)(wav)
+    return wav
+
+
+def tokenize_audio(tokenizer: AudioTokenizer, audio_path, offset=-1, num_frames=-1, multiple=320):
+    """data/tokenizer.py:141-159; `audio_path` may also be a float tensor [C, T] at the codec rate."""
+    if torch.is_tensor(audio_path):
+        wav, sr = audio_path, tokenizer.sample_rate
+    else:
+        wav, sr = load_wav(audio_path, offset, num_frames)
+    wav = pad_to_multiple(wav, multiple)
+    wav = convert_audio(wav, sr, tokenizer.sample_rate, tokenizer.channels)
+    wav = wav.unsqueeze(0)
+    with torch.no_grad():
+        encoded_frames, scale, emb = tokenizer.encode(wav)
+    return encoded_frames, scale, emb

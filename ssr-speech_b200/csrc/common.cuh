@@ -1,0 +1,137 @@
+// common.cuh — shared helpers for libssr_b200 (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+
+namespace ssrb {
+
+typedef __nv_bfloat16 bf16;
+
+// ---- error plumbing -------------------------------------------------------------------------
+void set_error(const std::string& msg);
+extern unsigned long long g_launch_count;   // kernels launched by this library (bench gpu_launches)
+
+#define SSRB_CUDA(expr)                                                                           \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            ::ssrb::set_error(std::string(#expr) + " -> " + cudaGetErrorString(_e) + " at " +     \
+                              __FILE__ + ":" + std::to_string(__LINE__));                         \
+            return 1;                                                                             \
+        }                                                                                         \
+    } while (0)
+
+#define SSRB_CHECK(cond, msg)                                                                     \
+    do {                                                                                          \
+        if (!(cond)) {                                                                            \
+            ::ssrb::set_error(std::string(msg) + " (" #cond ") at " + __FILE__ + ":" +            \
+                              std::to_string(__LINE__));                                          \
+            return 1;                                                                             \
+        }                                                                                         \
+    } while (0)
+
+#define SSRB_TRY(expr)                                                                            \
+    do {                                                                                          \
+        int _r = (expr);                                                                          \
+        if (_r) return _r;                                                                        \
+    } while (0)
+
+// every kernel launch goes through this so the launch count is honest
+#define SSRB_LAUNCH(kernel, grid, block, smem, stream, ...)                                       \
+    do {                                                                                          \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                               \
+        ::ssrb::g_launch_count++;                                                                 \
+        SSRB_CUDA(cudaGetLastError());                                                            \
+    } while (0)
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- device helpers -------------------------------------------------------------------------
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// 8 consecutive elements -> fp32 registers (16 B for bf16, 32 B for fp32); pointer must be 16B aligned
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+    float4 a = *reinterpret_cast<const float4*>(p);
+    float4 b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void load8(const bf16* p, float (&v)[8]) {
+    uint4 raw = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        v[2 * i] = __uint_as_float(w[i] << 16);
+        v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+}
+__device__ __forceinline__ void load4(const float* p, float (&v)[4]) {
+    float4 a = *reinterpret_cast<const float4*>(p);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+}
+__device__ __forceinline__ void load4(const bf16* p, float (&v)[4]) {
+    uint2 raw = *reinterpret_cast<const uint2*>(p);
+    v[0] = __uint_as_float(raw.x << 16); v[1] = __uint_as_float(raw.x & 0xffff0000u);
+    v[2] = __uint_as_float(raw.y << 16); v[3] = __uint_as_float(raw.y & 0xffff0000u);
+}
+__device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : expm1f(x); }
+
+// ---- GEMM interface (gemm_simt.cu / gemm_tc.cu) -----------------------------------------------------
+enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
+
+struct GemmArgs {
+    const void* A = nullptr;  int64_t lda = 0;          // [M, K] activations, dtype a_dtype
+    const void* W = nullptr;  int64_t ldw = 0;          // [N, K] weights, dtype w_dtype (same as A)
+    const float* bias = nullptr;                        // [N] or null
+    const float* residual = nullptr; int64_t ldr = 0;   // fp32 [M, N] or null (added after activation)
+    void* C = nullptr;        int64_t ldc = 0;          // [M, N], dtype c_dtype
+    int M = 0, N = 0, K = 0;
+    int act = ACT_NONE;
+    int ab_dtype = 0;                                   // SSRB_DTYPE_* of A and W
+    int c_dtype = 0;                                    // SSRB_DTYPE_* of C
+    // grouped GEMM (blockIdx.z): element strides between groups
+    int groups = 1;
+    int64_t a_gs = 0, w_gs = 0, bias_gs = 0, c_gs = 0;
+};
+
+int gemm_simt(const GemmArgs& g, cudaStream_t stream);
+// tcgen05 path: bf16 A/W only.  `workspace` (device, >= gemm_tc_workspace_bytes) is needed for split-K.
+int gemm_tc(const GemmArgs& g, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+size_t gemm_tc_workspace_bytes(int max_rows_decode, int max_n);
+bool gemm_tc_supported(const GemmArgs& g);
+
+}  // namespace ssrb

@@ -1,0 +1,565 @@
+// lm_engine.cu — the SSR-Speech decoder engine behind the C ABI (include/ssr_b200.h).
+//
+// Owns the packed weights, the in-place KV cache [layer][K|V][row][head][slot][128], the fp32 residual
+// stream and the per-utterance decode state.  One decode iteration of the reference's `while True`
+// loop (models/ssr.py:671-771) is enqueued as
+//     embed -> 16 x (LN1, QKV GEMM, KV append, attention, out-proj GEMM(+res), LN2, FFN1 GEMM(ReLU),
+//     FFN2 GEMM(+res)) -> final LN -> head GEMM(GELU) -> head GEMM -> sample/state kernel
+// and replayed as a CUDA graph, with no host synchronisation inside the loop.
+#include <map>
+#include <string>
+#include <vector>
+
+#include "lm_kernels.cuh"
+
+namespace ssrb {
+
+static thread_local std::string g_err;
+void set_error(const std::string& m) { g_err = m; }
+unsigned long long g_launch_count = 0;
+
+template <typename T>
+__global__ void convert_kernel(const float* __restrict__ src, T* __restrict__ dst, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) dst[i] = from_f32<T>(src[i]);
+}
+
+struct LayerW {
+    void *wqkv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr;
+    float *bqkv = nullptr, *bo = nullptr, *b1 = nullptr, *b2 = nullptr;
+    float *ln1w = nullptr, *ln1b = nullptr, *ln2w = nullptr, *ln2b = nullptr;
+};
+
+}  // namespace ssrb
+
+using namespace ssrb;
+
+struct ssrb_lm {
+    ssrb_lm_config cfg;
+    int device = 0;
+    int D, H, L, F, K, V, Vt, Hh;
+    int wdt;                 // weight / activation-operand / KV dtype
+    size_t esz;              // its element size
+    std::vector<LayerW> layers;
+    float *text_emb = nullptr, *audio_emb = nullptr, *pe = nullptr, *lnfw = nullptr, *lnfb = nullptr;
+    int n_pos = 0;
+    float alpha_t = 1.f, alpha_a = 1.f;
+    void *hw1 = nullptr, *hw2 = nullptr;       // [K*Hh, D], [K][V, Hh]
+    float *hb1 = nullptr, *hb2 = nullptr;
+    std::map<std::string, bool> loaded;
+    // workspace
+    int Mmax = 0;
+    float *x = nullptr, *qkv = nullptr, *logits = nullptr;
+    void *hn = nullptr, *ao = nullptr, *hid = nullptr, *hlast = nullptr, *hh = nullptr;
+    void *kcache = nullptr, *vcache = nullptr;
+    size_t kv_layer_elems = 0;
+    float* attn_ws = nullptr; int* tickets = nullptr;
+    void* tc_ws = nullptr; size_t tc_ws_bytes = 0;
+    PosDesc* d_desc = nullptr; int *d_rows = nullptr, *d_slots = nullptr;
+    int *d_row_ids = nullptr, *d_row_start = nullptr, *d_row_len = nullptr, *d_last_idx = nullptr;
+    UttState* d_state = nullptr; int *d_seq_len = nullptr, *d_next_tok = nullptr, *d_gen_tok = nullptr, *d_iter = nullptr;
+    float* staging = nullptr; size_t staging_elems = 0;
+    // batch
+    int n_utt = 0, rpu = 1, R = 0;
+    SampleParams sp{};
+    const float* noise = nullptr;
+    cudaGraphExec_t graph = nullptr;
+    bool use_graph = true;
+};
+
+static int dev_alloc(void** p, size_t bytes) {
+    SSRB_CUDA(cudaMalloc(p, bytes ? bytes : 16));
+    return 0;
+}
+
+const char* ssrb_last_error(void) { return g_err.c_str(); }
+int ssrb_version(void) { return 100; }
+uint64_t ssrb_launch_count(void) { return g_launch_count; }
+
+int ssrb_lm_create(const ssrb_lm_config* c, int device, ssrb_lm** out) {
+    SSRB_CHECK(c && out, "null argument");
+    SSRB_CHECK(c->d_model % 128 == 0 && c->d_model / c->n_head == 128, "head_dim must be 128");
+    SSRB_CHECK(c->d_model <= 2048, "d_model > 2048 not supported");
+    SSRB_CHECK(c->n_codebooks == 4, "n_codebooks must be 4");
+    SSRB_CHECK(c->weight_dtype == SSRB_DTYPE_F32 || c->weight_dtype == SSRB_DTYPE_BF16, "bad weight_dtype");
+    SSRB_CHECK(c->max_rows > 0 && c->max_seq > 0 && c->max_prefill_tokens > 0 && c->max_steps > 0, "bad capacity");
+    SSRB_CUDA(cudaSetDevice(device));
+    ssrb_lm* lm = new ssrb_lm();
+    lm->cfg = *c; lm->device = device;
+    lm->D = c->d_model; lm->H = c->n_head; lm->L = c->n_layer; lm->F = c->ffn_dim; lm->K = c->n_codebooks;
+    lm->V = c->n_audio_tokens; lm->Vt = c->n_text_tokens; lm->Hh = c->head_hidden;
+    lm->wdt = c->weight_dtype; lm->esz = c->weight_dtype == SSRB_DTYPE_F32 ? 4 : 2;
+    const char* ng = getenv("SSRB_NO_GRAPH");
+    lm->use_graph = !(ng && ng[0] == '1');
+    const int D = lm->D, F = lm->F, K = lm->K, V = lm->V, Hh = lm->Hh, L = lm->L;
+    const size_t e = lm->esz;
+    lm->layers.resize(L);
+    for (int n = 0; n < L; n++) {
+        LayerW& w = lm->layers[n];
+        SSRB_TRY(dev_alloc(&w.wqkv, (size_t)3 * D * D * e)); SSRB_TRY(dev_alloc(&w.wo, (size_t)D * D * e));
+        SSRB_TRY(dev_alloc(&w.w1, (size_t)F * D * e)); SSRB_TRY(dev_alloc(&w.w2, (size_t)D * F * e));
+        SSRB_TRY(dev_alloc((void**)&w.bqkv, 3 * D * 4)); SSRB_TRY(dev_alloc((void**)&w.bo, D * 4));
+        SSRB_TRY(dev_alloc((void**)&w.b1, F * 4)); SSRB_TRY(dev_alloc((void**)&w.b2, D * 4));
+        SSRB_TRY(dev_alloc((void**)&w.ln1w, D * 4)); SSRB_TRY(dev_alloc((void**)&w.ln1b, D * 4));
+        SSRB_TRY(dev_alloc((void**)&w.ln2w, D * 4)); SSRB_TRY(dev_alloc((void**)&w.ln2b, D * 4));
+    }
+    SSRB_TRY(dev_alloc((void**)&lm->text_emb, (size_t)lm->Vt * D * 4));
+    SSRB_TRY(dev_alloc((void**)&lm->audio_emb, (size_t)K * V * D * 4));
+    SSRB_TRY(dev_alloc((void**)&lm->lnfw, D * 4)); SSRB_TRY(dev_alloc((void**)&lm->lnfb, D * 4));
+    SSRB_TRY(dev_alloc(&lm->hw1, (size_t)K * Hh * D * e)); SSRB_TRY(dev_alloc(&lm->hw2, (size_t)K * V * Hh * e));
+    SSRB_TRY(dev_alloc((void**)&lm->hb1, K * Hh * 4)); SSRB_TRY(dev_alloc((void**)&lm->hb2, K * V * 4));
+    // workspace
+    const int R = c->max_rows;
+    lm->Mmax = c->max_prefill_tokens > R ? c->max_prefill_tokens : R;
+    const size_t M = lm->Mmax;
+    SSRB_TRY(dev_alloc((void**)&lm->x, M * D * 4)); SSRB_TRY(dev_alloc((void**)&lm->qkv, M * 3 * D * 4));
+    SSRB_TRY(dev_alloc(&lm->hn, M * D * e)); SSRB_TRY(dev_alloc(&lm->ao, M * D * e));
+    SSRB_TRY(dev_alloc(&lm->hid, M * F * e));
+    SSRB_TRY(dev_alloc(&lm->hlast, (size_t)R * D * e)); SSRB_TRY(dev_alloc(&lm->hh, (size_t)R * K * Hh * e));
+    SSRB_TRY(dev_alloc((void**)&lm->logits, (size_t)R * K * V * 4));
+    lm->kv_layer_elems = (size_t)R * lm->H * c->max_seq * 128;
+    SSRB_TRY(dev_alloc(&lm->kcache, lm->kv_layer_elems * L * e));
+    SSRB_TRY(dev_alloc(&lm->vcache, lm->kv_layer_elems * L * e));
+    SSRB_TRY(dev_alloc((void**)&lm->attn_ws, attn_decode_ws_floats(R, lm->H, c->max_seq) * 4));
+    SSRB_TRY(dev_alloc((void**)&lm->tickets, (size_t)R * lm->H * 4));
+    SSRB_CUDA(cudaMemset(lm->tickets, 0, (size_t)R * lm->H * 4));
+    lm->tc_ws_bytes = gemm_tc_workspace_bytes(R, 3 * D > F ? 3 * D : F);
+    SSRB_TRY(dev_alloc(&lm->tc_ws, lm->tc_ws_bytes));
+    SSRB_CUDA(cudaMemset(lm->tc_ws, 0, lm->tc_ws_bytes ? lm->tc_ws_bytes : 16));
+    SSRB_TRY(dev_alloc((void**)&lm->d_desc, M * sizeof(PosDesc)));
+    SSRB_TRY(dev_alloc((void**)&lm->d_rows, M * 4)); SSRB_TRY(dev_alloc((void**)&lm->d_slots, M * 4));
+    SSRB_TRY(dev_alloc((void**)&lm->d_row_ids, R * 4)); SSRB_TRY(dev_alloc((void**)&lm->d_row_start, R * 4));
+    SSRB_TRY(dev_alloc((void**)&lm->d_row_len, R * 4)); SSRB_TRY(dev_alloc((void**)&lm->d_last_idx, M * 4));
+    SSRB_TRY(dev_alloc((void**)&lm->d_state, R * sizeof(UttState)));
+    SSRB_TRY(dev_alloc((void**)&lm->d_seq_len, R * 4)); SSRB_TRY(dev_alloc((void**)&lm->d_next_tok, R * K * 4));
+    SSRB_TRY(dev_alloc((void**)&lm->d_gen_tok, (size_t)R * c->max_steps * K * 4));
+    SSRB_TRY(dev_alloc((void**)&lm->d_iter, 4));
+    *out = lm;
+    return 0;
+}
+
+void ssrb_lm_destroy(ssrb_lm* lm) {
+    if (!lm) return;
+    cudaSetDevice(lm->device);
+    cudaDeviceSynchronize();
+    if (lm->graph) cudaGraphExecDestroy(lm->graph);
+    for (auto& w : lm->layers) {
+        void* ps[] = {w.wqkv, w.wo, w.w1, w.w2, w.bqkv, w.bo, w.b1, w.b2, w.ln1w, w.ln1b, w.ln2w, w.ln2b};
+        for (void* p : ps) cudaFree(p);
+    }
+    void* ps[] = {lm->text_emb, lm->audio_emb, lm->pe, lm->lnfw, lm->lnfb, lm->hw1, lm->hw2, lm->hb1, lm->hb2, lm->x,
+                  lm->qkv, lm->logits, lm->hn, lm->ao, lm->hid, lm->hlast, lm->hh, lm->kcache, lm->vcache, lm->attn_ws,
+                  lm->tickets, lm->tc_ws, lm->d_desc, lm->d_rows, lm->d_slots, lm->d_row_ids, lm->d_row_start,
+                  lm->d_row_len, lm->d_last_idx, lm->d_state, lm->d_seq_len, lm->d_next_tok, lm->d_gen_tok, lm->d_iter,
+                  lm->staging};
+    for (void* p : ps) cudaFree(p);
+    delete lm;
+}
+
+// ---- weight loading -------------------------------------------------------------------------------
+static int upload(ssrb_lm* lm, const float* host, int64_t n, void* dst, int dst_dtype) {
+    if (dst_dtype == SSRB_DTYPE_F32) {
+        SSRB_CUDA(cudaMemcpy(dst, host, n * 4, cudaMemcpyHostToDevice));
+        return 0;
+    }
+    if ((size_t)n > lm->staging_elems) {
+        if (lm->staging) cudaFree(lm->staging);
+        lm->staging = nullptr; lm->staging_elems = 0;
+        SSRB_TRY(dev_alloc((void**)&lm->staging, n * 4));
+        lm->staging_elems = n;
+    }
+    SSRB_CUDA(cudaMemcpy(lm->staging, host, n * 4, cudaMemcpyHostToDevice));
+    SSRB_LAUNCH(convert_kernel<bf16>, 1024, 256, 0, 0, lm->staging, (bf16*)dst, n);
+    SSRB_CUDA(cudaDeviceSynchronize());
+    return 0;
+}
+
+static bool starts_with(const std::string& s, const char* p) { return s.rfind(p, 0) == 0; }
+
+int ssrb_lm_load_tensor(ssrb_lm* lm, const char* name_c, const float* host, const int64_t* shape, int ndim) {
+    SSRB_CHECK(lm && name_c && host, "null argument");
+    SSRB_CUDA(cudaSetDevice(lm->device));
+    const std::string name(name_c);
+    int64_t n = 1;
+    for (int i = 0; i < ndim; i++) n *= shape[i];
+    const int D = lm->D, F = lm->F, K = lm->K, V = lm->V, Hh = lm->Hh;
+    const int wdt = lm->wdt;
+    auto expect = [&](int64_t want) -> bool { return n == want; };
+#define SSRB_EXPECT(want) SSRB_CHECK(expect(want), ("shape mismatch for " + name).c_str())
+    if (name == "pe_table") {
+        SSRB_CHECK(ndim == 2 && shape[1] == D, "pe_table must be [n_pos, d_model]");
+        if (lm->pe) cudaFree(lm->pe);
+        SSRB_TRY(dev_alloc((void**)&lm->pe, n * 4));
+        lm->n_pos = (int)shape[0];
+        SSRB_TRY(upload(lm, host, n, lm->pe, SSRB_DTYPE_F32));
+    } else if (name == "text_embedding.word_embeddings.weight") {
+        SSRB_EXPECT((int64_t)lm->Vt * D); SSRB_TRY(upload(lm, host, n, lm->text_emb, SSRB_DTYPE_F32));
+    } else if (starts_with(name, "audio_embedding.")) {
+        const int k = atoi(name.c_str() + 16);
+        SSRB_CHECK(k >= 0 && k < K, "bad codebook index"); SSRB_EXPECT((int64_t)V * D);
+        SSRB_TRY(upload(lm, host, n, lm->audio_emb + (size_t)k * V * D, SSRB_DTYPE_F32));
+    } else if (name == "text_positional_embedding.alpha") { lm->alpha_t = host[0];
+    } else if (name == "audio_positional_embedding.alpha") { lm->alpha_a = host[0];
+    } else if (name == "decoder.norm.weight") { SSRB_EXPECT(D); SSRB_TRY(upload(lm, host, n, lm->lnfw, SSRB_DTYPE_F32));
+    } else if (name == "decoder.norm.bias") { SSRB_EXPECT(D); SSRB_TRY(upload(lm, host, n, lm->lnfb, SSRB_DTYPE_F32));
+    } else if (starts_with(name, "decoder.layers.")) {
+        const int nl = atoi(name.c_str() + 15);
+        SSRB_CHECK(nl >= 0 && nl < lm->L, "bad layer index");
+        LayerW& w = lm->layers[nl];
+        const std::string sub = name.substr(name.find('.', 15) + 1);
+        if (sub == "self_attn.in_proj_weight") { SSRB_EXPECT((int64_t)3 * D * D); SSRB_TRY(upload(lm, host, n, w.wqkv, wdt)); }
+        else if (sub == "self_attn.in_proj_bias") { SSRB_EXPECT(3 * D); SSRB_TRY(upload(lm, host, n, w.bqkv, 0)); }
+        else if (sub == "self_attn.out_proj.weight") { SSRB_EXPECT((int64_t)D * D); SSRB_TRY(upload(lm, host, n, w.wo, wdt)); }
+        else if (sub == "self_attn.out_proj.bias") { SSRB_EXPECT(D); SSRB_TRY(upload(lm, host, n, w.bo, 0)); }
+        else if (sub == "linear1.weight") { SSRB_EXPECT((int64_t)F * D); SSRB_TRY(upload(lm, host, n, w.w1, wdt)); }
+        else if (sub == "linear1.bias") { SSRB_EXPECT(F); SSRB_TRY(upload(lm, host, n, w.b1, 0)); }
+        else if (sub == "linear2.weight") { SSRB_EXPECT((int64_t)D * F); SSRB_TRY(upload(lm, host, n, w.w2, wdt)); }
+        else if (sub == "linear2.bias") { SSRB_EXPECT(D); SSRB_TRY(upload(lm, host, n, w.b2, 0)); }
+        else if (sub == "norm1.weight") { SSRB_EXPECT(D); SSRB_TRY(upload(lm, host, n, w.ln1w, 0)); }
+        else if (sub == "norm1.bias") { SSRB_EXPECT(D); SSRB_TRY(upload(lm, host, n, w.ln1b, 0)); }
+        else if (sub == "norm2.weight") { SSRB_EXPECT(D); SSRB_TRY(upload(lm, host, n, w.ln2w, 0)); }
+        else if (sub == "norm2.bias") { SSRB_EXPECT(D); SSRB_TRY(upload(lm, host, n, w.ln2b, 0)); }
+        else return 0;
+    } else if (starts_with(name, "predict_layer.")) {
+        const int k = atoi(name.c_str() + 14);
+        SSRB_CHECK(k >= 0 && k < K, "bad head index");
+        const std::string sub = name.substr(name.find('.', 14) + 1);
+        if (sub == "0.weight") { SSRB_EXPECT((int64_t)Hh * D); SSRB_TRY(upload(lm, host, n, (char*)lm->hw1 + (size_t)k * Hh * D * lm->esz, wdt)); }
+        else if (sub == "0.bias") { SSRB_EXPECT(Hh); SSRB_TRY(upload(lm, host, n, lm->hb1 + k * Hh, 0)); }
+        else if (sub == "2.weight") { SSRB_EXPECT((int64_t)V * Hh); SSRB_TRY(upload(lm, host, n, (char*)lm->hw2 + (size_t)k * V * Hh * lm->esz, wdt)); }
+        else if (sub == "2.bias") { SSRB_EXPECT(V); SSRB_TRY(upload(lm, host, n, lm->hb2 + k * V, 0)); }
+        else return 0;
+    } else {
+        return 0;   // keys that carry no inference state (e.g. accuracy_metrics.*) are ignored
+    }
+    lm->loaded[name] = true;
+    return 0;
+}
+
+int ssrb_lm_check_loaded(ssrb_lm* lm) {
+    std::vector<std::string> need = {"pe_table", "text_embedding.word_embeddings.weight", "text_positional_embedding.alpha",
+                                     "audio_positional_embedding.alpha", "decoder.norm.weight", "decoder.norm.bias"};
+    for (int k = 0; k < lm->K; k++) {
+        need.push_back("audio_embedding." + std::to_string(k) + ".word_embeddings.weight");
+        for (const char* s : {"0.weight", "0.bias", "2.weight", "2.bias"}) need.push_back("predict_layer." + std::to_string(k) + "." + s);
+    }
+    for (int n = 0; n < lm->L; n++)
+        for (const char* s : {"self_attn.in_proj_weight", "self_attn.in_proj_bias", "self_attn.out_proj.weight",
+                              "self_attn.out_proj.bias", "linear1.weight", "linear1.bias", "linear2.weight", "linear2.bias",
+                              "norm1.weight", "norm1.bias", "norm2.weight", "norm2.bias"})
+            need.push_back("decoder.layers." + std::to_string(n) + "." + s);
+    std::string missing;
+    for (auto& k : need) if (!lm->loaded.count(k)) missing += k + " ";
+    if (!missing.empty()) { set_error("missing tensors: " + missing); return 1; }
+    return 0;
+}
+
+// ---- GEMM dispatch ---------------------------------------------------------------------------------
+static int gemm(ssrb_lm* lm, GemmArgs g, cudaStream_t s) {
+    g.ab_dtype = lm->wdt;
+    if (lm->wdt == SSRB_DTYPE_BF16 && lm->cfg.gemm_impl != 1 && gemm_tc_supported(g))
+        return gemm_tc(g, lm->tc_ws, lm->tc_ws_bytes, s);
+    return gemm_simt(g, s);
+}
+
+// one decoder layer over M packed positions.  prefill: rows/slots/attn over packed rows; decode: M = R.
+static int run_layer(ssrb_lm* lm, int n, int M, bool prefill, int n_rows, int max_len, cudaStream_t s) {
+    const int D = lm->D, F = lm->F, H = lm->H;
+    const LayerW& w = lm->layers[n];
+    const size_t e = lm->esz;
+    void* kc = (char*)lm->kcache + (size_t)n * lm->kv_layer_elems * e;
+    void* vc = (char*)lm->vcache + (size_t)n * lm->kv_layer_elems * e;
+    SSRB_TRY(launch_layernorm(lm->x, nullptr, M, D, w.ln1w, w.ln1b, lm->hn, lm->wdt, s));
+    GemmArgs g;
+    g.A = lm->hn; g.lda = D; g.W = w.wqkv; g.ldw = D; g.bias = w.bqkv; g.C = lm->qkv; g.ldc = 3 * D;
+    g.M = M; g.N = 3 * D; g.K = D; g.c_dtype = SSRB_DTYPE_F32;
+    SSRB_TRY(gemm(lm, g, s));
+    if (prefill) {
+        SSRB_TRY(launch_kv_append(lm->qkv, M, D, H, lm->d_rows, lm->d_slots, nullptr, kc, vc, lm->wdt, lm->cfg.max_seq, s));
+        SSRB_TRY(launch_attn_prefill(lm->qkv, D, H, kc, vc, lm->wdt, lm->cfg.max_seq, n_rows, lm->d_row_ids,
+                                     lm->d_row_start, lm->d_row_len, max_len, lm->ao, lm->wdt, s));
+    } else {
+        SSRB_TRY(launch_kv_append(lm->qkv, M, D, H, nullptr, nullptr, lm->d_seq_len, kc, vc, lm->wdt, lm->cfg.max_seq, s));
+        SSRB_TRY(launch_attn_decode(lm->qkv, M, D, H, kc, vc, lm->wdt, lm->cfg.max_seq, lm->d_seq_len, lm->d_state,
+                                    lm->rpu, lm->attn_ws, lm->tickets, lm->ao, lm->wdt, s));
+    }
+    g = GemmArgs();
+    g.A = lm->ao; g.lda = D; g.W = w.wo; g.ldw = D; g.bias = w.bo; g.residual = lm->x; g.ldr = D; g.C = lm->x; g.ldc = D;
+    g.M = M; g.N = D; g.K = D; g.c_dtype = SSRB_DTYPE_F32;
+    SSRB_TRY(gemm(lm, g, s));
+    SSRB_TRY(launch_layernorm(lm->x, nullptr, M, D, w.ln2w, w.ln2b, lm->hn, lm->wdt, s));
+    g = GemmArgs();
+    g.A = lm->hn; g.lda = D; g.W = w.w1; g.ldw = D; g.bias = w.b1; g.C = lm->hid; g.ldc = F;
+    g.M = M; g.N = F; g.K = D; g.act = ACT_RELU; g.c_dtype = lm->wdt;
+    SSRB_TRY(gemm(lm, g, s));
+    g = GemmArgs();
+    g.A = lm->hid; g.lda = F; g.W = w.w2; g.ldw = F; g.bias = w.b2; g.residual = lm->x; g.ldr = D; g.C = lm->x; g.ldc = D;
+    g.M = M; g.N = D; g.K = F; g.c_dtype = SSRB_DTYPE_F32;
+    SSRB_TRY(gemm(lm, g, s));
+    return 0;
+}
+
+// final LN (gathered rows) + 4 prediction heads -> logits [M, K, V] fp32
+static int run_heads(ssrb_lm* lm, const int* gather_idx, int M, void* hl, void* hhbuf, float* logits, cudaStream_t s) {
+    const int D = lm->D, K = lm->K, V = lm->V, Hh = lm->Hh;
+    SSRB_TRY(launch_layernorm(lm->x, gather_idx, M, D, lm->lnfw, lm->lnfb, hl, lm->wdt, s));
+    GemmArgs g;
+    g.A = hl; g.lda = D; g.W = lm->hw1; g.ldw = D; g.bias = lm->hb1; g.C = hhbuf; g.ldc = K * Hh;
+    g.M = M; g.N = K * Hh; g.K = D; g.act = ACT_GELU; g.c_dtype = lm->wdt;
+    SSRB_TRY(gemm(lm, g, s));
+    g = GemmArgs();
+    g.A = hhbuf; g.lda = K * Hh; g.a_gs = Hh; g.W = lm->hw2; g.ldw = Hh; g.w_gs = (int64_t)V * Hh;
+    g.bias = lm->hb2; g.bias_gs = V; g.C = logits; g.ldc = (int64_t)K * V; g.c_gs = V;
+    g.M = M; g.N = V; g.K = Hh; g.groups = K; g.c_dtype = SSRB_DTYPE_F32;
+    SSRB_TRY(gemm(lm, g, s));
+    return 0;
+}
+
+static int enqueue_step(ssrb_lm* lm, cudaStream_t s) {
+    SSRB_TRY(launch_embed_step(lm->d_next_tok, lm->d_state, lm->R, lm->rpu, lm->K, lm->D, lm->audio_emb, lm->V, lm->pe,
+                               lm->alpha_a, lm->x, s));
+    for (int n = 0; n < lm->L; n++) SSRB_TRY(run_layer(lm, n, lm->R, false, 0, 0, s));
+    SSRB_TRY(run_heads(lm, nullptr, lm->R, lm->hlast, lm->hh, lm->logits, s));
+    SSRB_TRY(launch_sample(lm->logits, lm->d_state, lm->d_seq_len, lm->d_next_tok, lm->d_gen_tok, lm->noise, lm->d_iter,
+                           lm->sp, s));
+    return 0;
+}
+
+// ---- prefill ----------------------------------------------------------------------------------------
+struct RowPlan { int r, u, lx, plen, len; };
+
+static int prefill_chunk(ssrb_lm* lm, const std::vector<RowPlan>& rows, const ssrb_lm_batch* b, cudaStream_t s,
+                         const std::vector<int>* tf_audio /* teacher forcing: K*Ty tokens, no <mts> */) {
+    const int K = lm->K;
+    std::vector<PosDesc> desc; std::vector<int> prow, pslot, rid, rstart, rlen, last;
+    int M = 0, max_len = 0;
+    for (const RowPlan& rp : rows) {
+        rid.push_back(rp.r); rstart.push_back(M); rlen.push_back(rp.len);
+        if (rp.len > max_len) max_len = rp.len;
+        for (int i = 0; i < rp.len; i++) {
+            PosDesc pd{};
+            if (i < rp.lx) { pd.text_tok = b->text[(size_t)rp.r * b->text_stride + i]; pd.pe_idx = i; }
+            else {
+                const int j = i - rp.lx;
+                pd.text_tok = -1; pd.pe_idx = j;
+                int t[4];
+                for (int k = 0; k < K; k++) {
+                    if (tf_audio) t[k] = (*tf_audio)[(size_t)k * rp.plen + j];
+                    else if (j < rp.plen) t[k] = b->prompt[((size_t)rp.u * K + k) * b->prompt_stride + j];
+                    else t[k] = lm->cfg.mts;   // first <mts> of span 0 (ssr.py:654-660)
+                }
+                pd.a0 = t[0]; pd.a1 = t[1]; pd.a2 = t[2]; pd.a3 = t[3];
+                SSRB_CHECK(pd.pe_idx < lm->n_pos, "audio position exceeds the PE table");
+            }
+            desc.push_back(pd); prow.push_back(rp.r); pslot.push_back(i);
+        }
+        M += rp.len;
+        last.push_back(M - 1);
+    }
+    SSRB_CHECK(M <= lm->Mmax, "prefill chunk exceeds max_prefill_tokens");
+    SSRB_CUDA(cudaMemcpyAsync(lm->d_desc, desc.data(), M * sizeof(PosDesc), cudaMemcpyHostToDevice, s));
+    SSRB_CUDA(cudaMemcpyAsync(lm->d_rows, prow.data(), M * 4, cudaMemcpyHostToDevice, s));
+    SSRB_CUDA(cudaMemcpyAsync(lm->d_slots, pslot.data(), M * 4, cudaMemcpyHostToDevice, s));
+    SSRB_CUDA(cudaMemcpyAsync(lm->d_row_ids, rid.data(), rid.size() * 4, cudaMemcpyHostToDevice, s));
+    SSRB_CUDA(cudaMemcpyAsync(lm->d_row_start, rstart.data(), rid.size() * 4, cudaMemcpyHostToDevice, s));
+    SSRB_CUDA(cudaMemcpyAsync(lm->d_row_len, rlen.data(), rid.size() * 4, cudaMemcpyHostToDevice, s));
+    SSRB_CUDA(cudaMemcpyAsync(lm->d_last_idx, last.data(), last.size() * 4, cudaMemcpyHostToDevice, s));
+    SSRB_CUDA(cudaStreamSynchronize(s));   // host vectors go out of scope
+    SSRB_TRY(launch_embed_prefill(lm->d_desc, M, lm->D, lm->text_emb, lm->audio_emb, lm->V, lm->pe, lm->alpha_t,
+                                  lm->alpha_a, lm->x, s));
+    for (int n = 0; n < lm->L; n++) SSRB_TRY(run_layer(lm, n, M, true, (int)rows.size(), max_len, s));
+    if (!tf_audio) {
+        // final LN of each row's last position -> hlast[row] (rows of a chunk are consecutive)
+        SSRB_TRY(launch_layernorm(lm->x, lm->d_last_idx, (int)rows.size(), lm->D, lm->lnfw, lm->lnfb,
+                                  (char*)lm->hlast + (size_t)rows[0].r * lm->D * lm->esz, lm->wdt, s));
+    }
+    return 0;
+}
+
+int ssrb_lm_begin(ssrb_lm* lm, const ssrb_lm_batch* b, const ssrb_sampling* sp, const float* noise_dev, void* stream) {
+    SSRB_CHECK(lm && b && sp, "null argument");
+    SSRB_CUDA(cudaSetDevice(lm->device));
+    SSRB_TRY(ssrb_lm_check_loaded(lm));
+    cudaStream_t s = (cudaStream_t)stream;
+    const int rpu = sp->aug_text ? 2 : 1;
+    const int U = b->n_utt, R = U * rpu, K = lm->K;
+    SSRB_CHECK(U > 0 && R <= lm->cfg.max_rows, "batch exceeds max_rows");
+    SSRB_CHECK(sp->cfg_coef >= 1.0f, "cfg_coef must be >= 1.0");           // ssr.py:552
+    SSRB_CHECK(sp->n_silence <= SSRB_MAX_SILENCE, "too many silence tokens");
+    lm->n_utt = U; lm->rpu = rpu; lm->R = R; lm->noise = noise_dev;
+    if (lm->graph) { cudaGraphExecDestroy(lm->graph); lm->graph = nullptr; }
+    SampleParams& p = lm->sp;
+    p.K = K; p.V = lm->V; p.rpu = rpu; p.empty_token = lm->cfg.empty_token; p.eog = lm->cfg.eog; p.eos = lm->cfg.eos;
+    p.sos = lm->cfg.sos; p.mts = lm->cfg.mts; p.max_n_spans = lm->cfg.max_n_spans; p.top_k = sp->top_k; p.top_p = sp->top_p;
+    p.temperature = sp->temperature; p.stop_repetition = sp->stop_repetition; p.n_silence = sp->n_silence;
+    for (int i = 0; i < sp->n_silence; i++) p.silence[i] = sp->silence_tokens[i];
+    p.cfg_coef = sp->cfg_coef; p.cfg_stride = sp->cfg_stride; p.seed = sp->seed; p.max_steps = lm->cfg.max_steps; p.n_utt = U;
+    // state + plans
+    std::vector<UttState> st(U); std::vector<int> seq(R); std::vector<RowPlan> plan;
+    for (int u = 0; u < U; u++) {
+        const int lx = b->text_len[u], pl = b->prompt_len[u];
+        SSRB_CHECK(lx > 0 && lx <= b->text_stride && pl >= 0 && pl <= b->prompt_stride, "bad text/prompt length");
+        SSRB_CHECK(b->n_spans[u] >= 1 && b->n_spans[u] <= lm->cfg.max_n_spans, "n_spans out of range");
+        SSRB_CHECK(lx + pl + 1 + lm->cfg.max_steps <= lm->cfg.max_seq, "max_seq too small for text + prompt + max_steps");
+        SSRB_CHECK(pl + 1 + lm->cfg.max_steps <= lm->n_pos && lx <= lm->n_pos, "PE table too small");
+        UttState z{}; z.cfg_tag = 1; z.prev_token = -1; z.n_spans = b->n_spans[u]; z.x_len = lx; z.y_len = pl;
+        st[u] = z;
+        for (int j = 0; j < rpu; j++) { seq[u * rpu + j] = lx + pl; plan.push_back({u * rpu + j, u, lx, pl, lx + pl + 1}); }
+    }
+    SSRB_CUDA(cudaMemcpyAsync(lm->d_state, st.data(), U * sizeof(UttState), cudaMemcpyHostToDevice, s));
+    SSRB_CUDA(cudaMemcpyAsync(lm->d_seq_len, seq.data(), R * 4, cudaMemcpyHostToDevice, s));
+    SSRB_CUDA(cudaMemsetAsync(lm->d_iter, 0, 4, s));
+    SSRB_CUDA(cudaStreamSynchronize(s));
+    // chunked prefill
+    std::vector<RowPlan> chunk; int tok = 0;
+    for (size_t i = 0; i < plan.size(); i++) {
+        SSRB_CHECK(plan[i].len <= lm->cfg.max_prefill_tokens, "one prompt exceeds max_prefill_tokens");
+        if (tok + plan[i].len > lm->cfg.max_prefill_tokens) { SSRB_TRY(prefill_chunk(lm, chunk, b, s, nullptr)); chunk.clear(); tok = 0; }
+        chunk.push_back(plan[i]); tok += plan[i].len;
+    }
+    if (!chunk.empty()) SSRB_TRY(prefill_chunk(lm, chunk, b, s, nullptr));
+    // heads on every row's last position, then iteration 1's sample
+    const int D = lm->D, V = lm->V, Hh = lm->Hh;
+    GemmArgs g;
+    g.A = lm->hlast; g.lda = D; g.W = lm->hw1; g.ldw = D; g.bias = lm->hb1; g.C = lm->hh; g.ldc = K * Hh;
+    g.M = R; g.N = K * Hh; g.K = D; g.act = ACT_GELU; g.c_dtype = lm->wdt;
+    SSRB_TRY(gemm(lm, g, s));
+    g = GemmArgs();
+    g.A = lm->hh; g.lda = K * Hh; g.a_gs = Hh; g.W = lm->hw2; g.ldw = Hh; g.w_gs = (int64_t)V * Hh;
+    g.bias = lm->hb2; g.bias_gs = V; g.C = lm->logits; g.ldc = (int64_t)K * V; g.c_gs = V;
+    g.M = R; g.N = V; g.K = Hh; g.groups = K; g.c_dtype = SSRB_DTYPE_F32;
+    SSRB_TRY(gemm(lm, g, s));
+    SSRB_TRY(launch_sample(lm->logits, lm->d_state, lm->d_seq_len, lm->d_next_tok, lm->d_gen_tok, lm->noise, lm->d_iter,
+                           lm->sp, s));
+    return 0;
+}
+
+int ssrb_lm_decode(ssrb_lm* lm, int n_steps, void* stream) {
+    SSRB_CHECK(lm && lm->R > 0, "ssrb_lm_begin has not been called");
+    SSRB_CUDA(cudaSetDevice(lm->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!lm->use_graph) {
+        for (int i = 0; i < n_steps; i++) SSRB_TRY(enqueue_step(lm, s));
+        return 0;
+    }
+    if (!lm->graph) {
+        cudaStream_t cs;
+        SSRB_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+        cudaGraph_t gr = nullptr;
+        SSRB_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+        const int rc = enqueue_step(lm, cs);
+        cudaError_t ce = cudaStreamEndCapture(cs, &gr);
+        cudaStreamDestroy(cs);
+        if (rc) { if (gr) cudaGraphDestroy(gr); return rc; }
+        SSRB_CUDA(ce);
+        SSRB_CUDA(cudaGraphInstantiate(&lm->graph, gr, 0));
+        cudaGraphDestroy(gr);
+    }
+    for (int i = 0; i < n_steps; i++) SSRB_CUDA(cudaGraphLaunch(lm->graph, s));
+    return 0;
+}
+
+int ssrb_lm_poll(ssrb_lm* lm, void* stream, int* n_done, int* n_iter) {
+    SSRB_CHECK(lm && lm->n_utt > 0, "no active batch");
+    cudaStream_t s = (cudaStream_t)stream;
+    std::vector<UttState> st(lm->n_utt);
+    int it = 0;
+    SSRB_CUDA(cudaMemcpyAsync(st.data(), lm->d_state, lm->n_utt * sizeof(UttState), cudaMemcpyDeviceToHost, s));
+    SSRB_CUDA(cudaMemcpyAsync(&it, lm->d_iter, 4, cudaMemcpyDeviceToHost, s));
+    SSRB_CUDA(cudaStreamSynchronize(s));
+    int d = 0;
+    for (auto& x : st) d += x.done ? 1 : 0;
+    if (n_done) *n_done = d;
+    if (n_iter) *n_iter = it;
+    return 0;
+}
+
+int ssrb_lm_read_tokens(ssrb_lm* lm, void* stream, int utt, int32_t* out, int cap, int* n_tokens, int32_t* span_len) {
+    SSRB_CHECK(lm && utt >= 0 && utt < lm->n_utt, "bad utterance index");
+    cudaStream_t s = (cudaStream_t)stream;
+    UttState st;
+    SSRB_CUDA(cudaMemcpyAsync(&st, lm->d_state + utt, sizeof(UttState), cudaMemcpyDeviceToHost, s));
+    SSRB_CUDA(cudaStreamSynchronize(s));
+    SSRB_CHECK(st.n_tok <= cap, "token buffer too small");
+    SSRB_CUDA(cudaMemcpyAsync(out, lm->d_gen_tok + (size_t)utt * lm->cfg.max_steps * lm->K, (size_t)st.n_tok * lm->K * 4,
+                              cudaMemcpyDeviceToHost, s));
+    SSRB_CUDA(cudaStreamSynchronize(s));
+    if (n_tokens) *n_tokens = st.n_tok;
+    if (span_len) for (int i = 0; i < SSRB_MAX_SPANS; i++) span_len[i] = st.span_len[i];
+    return 0;
+}
+
+int ssrb_lm_read_logits(ssrb_lm* lm, void* stream, float* host_out) {
+    SSRB_CHECK(lm && lm->R > 0 && host_out, "no active batch");
+    cudaStream_t s = (cudaStream_t)stream;
+    SSRB_CUDA(cudaMemcpyAsync(host_out, lm->logits, (size_t)lm->R * lm->K * lm->V * 4, cudaMemcpyDeviceToHost, s));
+    SSRB_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int ssrb_lm_teacher_forced(ssrb_lm* lm, const int32_t* text, int Lx, const int32_t* audio, int Ty, float* host_logits,
+                           void* stream) {
+    SSRB_CHECK(lm && text && audio && host_logits, "null argument");
+    SSRB_CUDA(cudaSetDevice(lm->device));
+    SSRB_TRY(ssrb_lm_check_loaded(lm));
+    cudaStream_t s = (cudaStream_t)stream;
+    SSRB_CHECK(Lx + Ty <= lm->cfg.max_prefill_tokens && Lx + Ty <= lm->cfg.max_seq, "sequence too long for teacher forcing");
+    SSRB_CHECK(Ty <= lm->n_pos && Lx <= lm->n_pos, "PE table too small");
+    ssrb_lm_batch b{};
+    b.n_utt = 1; b.text = text; b.text_stride = Lx;
+    std::vector<int> aud(audio, audio + (size_t)lm->K * Ty);
+    std::vector<RowPlan> rows = {{0, 0, Lx, Ty, Lx + Ty}};
+    lm->rpu = 1;
+    SSRB_TRY(prefill_chunk(lm, rows, &b, s, &aud));
+    // heads over all audio positions
+    const int K = lm->K, V = lm->V, Hh = lm->Hh, D = lm->D;
+    void *hl = nullptr, *hhb = nullptr; float* lg = nullptr; int* idx = nullptr;
+    SSRB_TRY(dev_alloc(&hl, (size_t)Ty * D * lm->esz)); SSRB_TRY(dev_alloc(&hhb, (size_t)Ty * K * Hh * lm->esz));
+    SSRB_TRY(dev_alloc((void**)&lg, (size_t)Ty * K * V * 4)); SSRB_TRY(dev_alloc((void**)&idx, Ty * 4));
+    std::vector<int> hidx(Ty);
+    for (int i = 0; i < Ty; i++) hidx[i] = Lx + i;
+    SSRB_CUDA(cudaMemcpyAsync(idx, hidx.data(), Ty * 4, cudaMemcpyHostToDevice, s));
+    SSRB_CUDA(cudaStreamSynchronize(s));
+    int rc = run_heads(lm, idx, Ty, hl, hhb, lg, s);
+    if (!rc) {
+        cudaError_t ce = cudaMemcpyAsync(host_logits, lg, (size_t)Ty * K * V * 4, cudaMemcpyDeviceToHost, s);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+        if (ce != cudaSuccess) { set_error(cudaGetErrorString(ce)); rc = 1; }
+    }
+    cudaFree(hl); cudaFree(hhb); cudaFree(lg); cudaFree(idx);
+    return rc;
+}
+
+int ssrb_lm_step_bytes(ssrb_lm* lm, void* stream, double* weight_bytes, double* kv_bytes) {
+    SSRB_CHECK(lm && lm->n_utt > 0, "no active batch");
+    cudaStream_t s = (cudaStream_t)stream;
+    std::vector<UttState> st(lm->n_utt); std::vector<int> seq(lm->R);
+    SSRB_CUDA(cudaMemcpyAsync(st.data(), lm->d_state, lm->n_utt * sizeof(UttState), cudaMemcpyDeviceToHost, s));
+    SSRB_CUDA(cudaMemcpyAsync(seq.data(), lm->d_seq_len, lm->R * 4, cudaMemcpyDeviceToHost, s));
+    SSRB_CUDA(cudaStreamSynchronize(s));
+    const double D = lm->D, F = lm->F, K = lm->K, V = lm->V, Hh = lm->Hh, L = lm->L, e = (double)lm->esz;
+    // W_step = per-layer matrices + biases + LN + final LN + heads, streamed once per step
+    const double per_layer = (3 * D * D + D * D + 2 * D * F) * e + (3 * D + D + F + D + 4 * D) * 4.0;
+    const double heads = (K * Hh * D + K * V * Hh) * e + (K * Hh + K * V) * 4.0;
+    if (weight_bytes) *weight_bytes = L * per_layer + 2 * D * 4.0 + heads;
+    double kv = 0;
+    for (int r = 0; r < lm->R; r++)
+        if (!st[r / lm->rpu].done) kv += L * 2.0 * D * e * ((double)seq[r] + 1.0 /*read S+1*/ + 1.0 /*write 1*/);
+    if (kv_bytes) *kv_bytes = kv;
+    return 0;
+}
+
+int ssrb_op_gemm(const void* A, const void* W, const float* bias, const float* residual, float* C, int M, int N, int K,
+                 int dtype, int act, int impl, void* stream) {
+    GemmArgs g;
+    g.A = A; g.lda = K; g.W = W; g.ldw = K; g.bias = bias; g.residual = residual; g.ldr = N; g.C = C; g.ldc = N;
+    g.M = M; g.N = N; g.K = K; g.act = act; g.ab_dtype = dtype; g.c_dtype = SSRB_DTYPE_F32;
+    if (impl == 2) {
+        SSRB_CHECK(dtype == SSRB_DTYPE_BF16 && gemm_tc_supported(g), "tcgen05 GEMM does not support this problem");
+        static void* ws = nullptr; static size_t wsb = 0;
+        if (!ws) { wsb = gemm_tc_workspace_bytes(256, 16384); SSRB_CUDA(cudaMalloc(&ws, wsb)); SSRB_CUDA(cudaMemset(ws, 0, wsb)); }
+        return gemm_tc(g, ws, wsb, (cudaStream_t)stream);
+    }
+    return gemm_simt(g, (cudaStream_t)stream);
+}

@@ -1,0 +1,58 @@
+// lm_kernels.cuh — launch wrappers of the LM kernels (lm_kernels.cu), used by lm_engine.cu.
+#pragma once
+#include "common.cuh"
+#include "../../include/ssr_b200.h"
+
+namespace ssrb {
+
+// per-utterance decode state — the Python locals of the reference's span loop (models/ssr.py:647-652)
+// plus batch bookkeeping.  Lives on the device; the host only polls `done`.
+struct UttState {
+    int num_gen, num_eog, cfg_tag, prev_token, consec_silence;   // ssr.py:647-652
+    int span_idx, n_spans, done;
+    int x_len;        // text length (length guard ssr.py:739)
+    int y_len;        // audio positions already in the KV cache
+    int n_tok;        // iterations recorded so far (all spans)
+    int span_len[SSRB_MAX_SPANS];
+};
+
+struct SampleParams {
+    int K, V;                       // codebooks, audio classes
+    int rpu;                        // rows per utterance (2 with CFG)
+    int empty_token, eog, eos, sos, mts, max_n_spans;
+    int top_k; float top_p; float temperature;
+    int stop_repetition; int n_silence; int silence[SSRB_MAX_SILENCE];
+    float cfg_coef; int cfg_stride;
+    unsigned long long seed;
+    int max_steps;
+    int n_utt;
+};
+
+// packed prompt position descriptor for the prefill embedding (host-built)
+struct PosDesc { int text_tok; int a0, a1, a2, a3; int pe_idx; };   // text_tok >= 0 -> text position
+
+int launch_embed_prefill(const PosDesc* desc, int M, int D, const float* text_emb, const float* audio_emb, int V,
+                         const float* pe, float alpha_t, float alpha_a, float* x, cudaStream_t s);
+int launch_embed_step(const int* next_tok, const UttState* st, int R, int rpu, int K, int D, const float* audio_emb,
+                      int V, const float* pe, float alpha_a, float* x, cudaStream_t s);
+// y[m] = LN(x[idx ? idx[m] : m]); out dtype SSRB_DTYPE_*
+int launch_layernorm(const float* x, const int* idx, int M, int D, const float* w, const float* b, void* out,
+                     int out_dtype, cudaStream_t s);
+// scatter K/V of qkv[M,3D] into cache[(kv, r, h, slot, d)]; rows/slots null => r = m, slot = seq_len[m]
+int launch_kv_append(const float* qkv, int M, int D, int H, const int* rows, const int* slots, const int* seq_len,
+                     void* kcache, void* vcache, int cache_dtype, int Smax, cudaStream_t s);
+// single-query attention against the cache (decode); out [R, D] in act dtype
+int launch_attn_decode(const float* qkv, int R, int D, int H, const void* kcache, const void* vcache, int cache_dtype,
+                       int Smax, const int* seq_len, const UttState* st, int rpu, float* ws, int* tickets,
+                       void* out, int out_dtype, cudaStream_t s);
+size_t attn_decode_ws_floats(int R, int H, int Smax);
+int attn_decode_nsplit(int Smax);
+// causal attention over packed prompt rows (prefill); K/V read from the cache
+int launch_attn_prefill(const float* qkv, int D, int H, const void* kcache, const void* vcache, int cache_dtype,
+                        int Smax, int n_rows, const int* row_ids, const int* row_start, const int* row_len,
+                        int max_len, void* out, int out_dtype, cudaStream_t s);
+// CFG + logit rules + top-k/top-p + sample + state machine (models/ssr.py:690-754)
+int launch_sample(const float* logits, UttState* st, int* seq_len, int* next_tok, int* gen_tok, const float* noise,
+                  int* iter_counter, const SampleParams& p, cudaStream_t s);
+
+}  // namespace ssrb

@@ -1,0 +1,332 @@
+"""`SSR_Speech` — drop-in for the inference path of reference models/ssr.py::SSR_Speech.
+
+Same constructor (`SSR_Speech(args)` with the Namespace stored in ``ckpt["config"]``), same
+``load_state_dict`` keys, same ``inference(...)`` signature, assertions and
+return values (models/ssr.py:504-524, :552-561, :804-812).  Host-side sequence surgery lives in
+`seq.py`; everything between the prologue and the epilogue — embeddings, 16 decoder layers with an
+in-place KV cache, prediction heads, CFG, logit rules, top-k/top-p sampling and the EOG/span state
+machine — runs inside libssr_b200.so as sm_100a kernels replayed from a CUDA graph.
+
+Extension over the reference (which asserts batch 1, ssr.py:559-561): `inference_batch` decodes many
+utterances at once; utterance i behaves exactly like an independent `inference` call.
+"""
+from __future__ import annotations
+
+import copy
+import ctypes as C
+import os
+from argparse import Namespace
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib, seq
+from .config import SSRConfig
+
+_PE_MIN = 4000   # reference starts with a 4000-position table and auto-extends (embedding.py:67-92)
+
+
+def sinusoid_table(n_pos: int, dim: int) -> torch.Tensor:
+    """Same construction as models/modules/embedding.py:76-92 (fp32 torch CPU ops)."""
+    import math
+    pos = torch.arange(0, n_pos, dtype=torch.float32).unsqueeze(1)
+    div = torch.exp(torch.arange(0, dim, 2, dtype=torch.float32) * -(math.log(10000.0) / dim))
+    pe = torch.zeros(n_pos, dim)
+    pe[:, 0::2] = torch.sin(pos * div)
+    pe[:, 1::2] = torch.cos(pos * div)
+    return pe
+
+
+class SSR_Speech:
+    def __init__(self, args: Optional[Namespace] = None, config: Optional[Dict] = None, precision: Optional[str] = None,
+                 gemm_impl: int = 0):
+        if args is None:
+            if config is None:
+                raise ValueError("Either `args` or `config` must be provided.")
+            args = Namespace(**config)
+        elif config is not None:
+            raise ValueError("Cannot provide both `args` and `config`.")
+        self.args = copy.copy(args)
+        self.cfg = SSRConfig.from_args(args)
+        # mirror the attribute normalisation of ssr.py:113-119
+        self.args.n_special = self.cfg.n_special
+        self.args.eos = self.cfg.eos
+        self.args.audio_vocab_size = self.cfg.audio_vocab_size
+        self.n_text_tokens = self.cfg.n_text_tokens
+        self.n_audio_tokens = [self.cfg.n_audio_tokens] * self.cfg.n_codebooks
+        precision = precision or os.environ.get("SSRB_PRECISION", "bf16")
+        assert precision in ("bf16", "fp32"), precision
+        self.precision = precision
+        self.gemm_impl = int(os.environ.get("SSRB_GEMM_IMPL", gemm_impl))
+        self._sd: Optional[Dict[str, torch.Tensor]] = None
+        self._device: Optional[torch.device] = None
+        self._h = None           # ssrb_lm*
+        self._cap = None         # (max_rows, max_seq, max_prefill_tokens, max_steps)
+        self.training = False
+        self.last_stats: Dict[str, float] = {}
+
+    # ---- nn.Module-like surface used by inference_v2.py:198-204 -------------------------------------
+    def load_state_dict(self, state_dict, strict: bool = True):
+        sd = {k: v.detach().to("cpu", torch.float32).contiguous() for k, v in state_dict.items() if torch.is_tensor(v)}
+        need = ["text_embedding.word_embeddings.weight", "decoder.norm.weight", "predict_layer.0.0.weight"]
+        missing = [k for k in need if k not in sd]
+        if missing and strict:
+            raise RuntimeError(f"Missing key(s) in state_dict: {missing}")
+        self._sd = sd
+        self._destroy()
+        return torch.nn.modules.module._IncompatibleKeys(missing, [])
+
+    def state_dict(self):
+        return dict(self._sd or {})
+
+    def to(self, device):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("ssr_speech_b200.SSR_Speech runs on CUDA devices only (no CPU fallback)")
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        if self._device != device:
+            self._destroy()
+        self._device = device
+        return self
+
+    def cuda(self, index=None):
+        return self.to(torch.device("cuda", index if index is not None else torch.cuda.current_device()))
+
+    def eval(self):
+        self.training = False
+        return self
+
+    def __del__(self):
+        try:
+            self._destroy()
+        except Exception:
+            pass
+
+    def _destroy(self):
+        if self._h is not None:
+            _lib.load().ssrb_lm_destroy(self._h)
+            self._h = None
+            self._cap = None
+
+    # ---- engine management ----------------------------------------------------------------------------
+    def _ensure_engine(self, rows: int, max_seq: int, prefill_tokens: int, max_steps: int):
+        if self._sd is None:
+            raise RuntimeError("load_state_dict must be called before inference")
+        if self._device is None:
+            raise RuntimeError("call .to('cuda') before inference (no CPU fallback)")
+        cap = self._cap
+        if self._h is not None and cap[0] >= rows and cap[1] >= max_seq and cap[2] >= prefill_tokens and cap[3] >= max_steps:
+            return
+        if cap is not None:   # grow-only
+            rows, max_seq = max(rows, cap[0]), max(max_seq, cap[1])
+            prefill_tokens, max_steps = max(prefill_tokens, cap[2]), max(max_steps, cap[3])
+        self._destroy()
+        lib = _lib.load()
+        c = self.cfg
+        conf = _lib.LMConfig(
+            d_model=c.d_model, n_head=c.nhead, n_layer=c.num_decoder_layers, ffn_dim=c.ffn_dim, n_codebooks=c.n_codebooks,
+            n_audio_tokens=c.n_audio_tokens, n_text_tokens=c.n_text_tokens, head_hidden=c.head_hidden,
+            empty_token=c.empty_token, eog=c.eog, eos=c.eos, sos=c.sos, mts=c.mts, max_n_spans=c.max_n_spans,
+            max_rows=rows, max_seq=max_seq, max_prefill_tokens=prefill_tokens, max_steps=max_steps,
+            weight_dtype=_lib.SSRB_DTYPE_BF16 if self.precision == "bf16" else _lib.SSRB_DTYPE_F32,
+            gemm_impl=self.gemm_impl)
+        h = C.c_void_p()
+        with torch.cuda.device(self._device):
+            _lib.check(lib.ssrb_lm_create(C.byref(conf), self._device.index, C.byref(h)), "ssrb_lm_create")
+            self._h = h
+            _lib.load_state_dict_into(lib.ssrb_lm_load_tensor, h, self._sd)
+            n_pos = max(_PE_MIN, max_seq + 8)
+            _lib.load_state_dict_into(lib.ssrb_lm_load_tensor, h, {"pe_table": sinusoid_table(n_pos, c.d_model)})
+            _lib.check(lib.ssrb_lm_check_loaded(h), "ssrb_lm_check_loaded")
+        self._cap = (rows, max_seq, prefill_tokens, max_steps)
+
+    def reserve(self, n_utt: int, text_len: int, prompt_frames: int, aug_text: bool = True, n_spans: int = 1):
+        """Optional: pre-build the engine for a given batch geometry (weights upload + allocations)."""
+        rpu = 2 if aug_text else 1
+        steps = self._max_steps(text_len, prompt_frames + 8, n_spans)
+        s0 = text_len + prompt_frames + 8
+        self._ensure_engine(n_utt * rpu, s0 + steps + 8, min(max(s0, 16384), max(s0, s0 * n_utt * rpu)), steps)
+
+    def _max_steps(self, x_len: int, prompt_len: int, n_spans: int) -> int:
+        K = self.cfg.n_codebooks
+        return n_spans * (max(10 * x_len - prompt_len, 0) + 2 + K) + 4
+
+    # ---- the reference API ---------------------------------------------------------------------------------
+    @torch.no_grad()
+    def inference(self, x: torch.Tensor, x_lens: torch.Tensor, prompt_x: torch.Tensor, prompt_x_lens: torch.Tensor,
+                  y: torch.Tensor, prompt: torch.Tensor, mask_interval: torch.Tensor, top_k: int = -100,
+                  top_p: float = 1.0, temperature: float = 1.0, stop_repetition: int = -1, kvcache: int = 1,
+                  silence_tokens: Sequence[int] = (1388, 1898, 131), cfg_coef: float = 1.5, cfg_stride: int = 1,
+                  aug_text: bool = False, aug_context: bool = False, cfg_pretrained: bool = False,
+                  _uncond_x: Optional[torch.Tensor] = None, _noise: Optional[torch.Tensor] = None):
+        """Same contract as reference models/ssr.py:504-812 (batch 1).  `kvcache` is accepted for
+        compatibility: the engine always decodes incrementally (the reference produces identical tokens
+        either way).  `_uncond_x` / `_noise` are parity-test hooks."""
+        assert cfg_coef >= 1.0, cfg_coef
+        assert x.ndim == 2, x.shape
+        assert x_lens.ndim == 1, x_lens.shape
+        assert y.ndim == 3, y.shape
+        assert prompt.ndim == 3, prompt.shape
+        K = self.cfg.n_codebooks
+        assert y.shape[0] == 1 and y.shape[2] == K, y.shape
+        assert prompt.shape[0] == 1 and prompt.shape[2] == K, prompt.shape
+        assert mask_interval.shape == torch.Size((1, mask_interval.shape[1], 2)), mask_interval
+        out = self.inference_batch(
+            [x[0]], [y[0]], [mask_interval[0]], prompt_xs=[prompt_x[0]], prompts=[prompt[0]], top_k=top_k, top_p=top_p,
+            temperature=temperature, stop_repetition=stop_repetition, silence_tokens=silence_tokens, cfg_coef=cfg_coef,
+            cfg_stride=cfg_stride, aug_text=aug_text, aug_context=aug_context, cfg_pretrained=cfg_pretrained,
+            uncond_xs=None if _uncond_x is None else [_uncond_x], noise=_noise, device=y.device)
+        return out[0]
+
+    @torch.no_grad()
+    def inference_batch(self, xs: List[torch.Tensor], ys: List[torch.Tensor], mask_intervals: List, prompt_xs=None,
+                        prompts=None, top_k: int = -100, top_p: float = 1.0, temperature: float = 1.0,
+                        stop_repetition: int = -1, silence_tokens: Sequence[int] = (1388, 1898, 131),
+                        cfg_coef: float = 1.5, cfg_stride: int = 1, aug_text: bool = False, aug_context: bool = False,
+                        cfg_pretrained: bool = False, uncond_xs=None, noise: Optional[torch.Tensor] = None,
+                        seed: Optional[int] = None, device=None, poll_every: int = 16):
+        """xs[i]: [Lx_i] int64 phoneme ids; ys[i]: [T_i, K] int64 codes; mask_intervals[i]: [M_i, 2].
+        Returns a list of (res [1,K,T_new] int64 (device), marks [1,T_new] int64 (CPU), masks, non_mask_intervals)."""
+        if cfg_pretrained:
+            raise NotImplementedError("cfg_pretrained=True (key-padding on the uncond row, ssr.py:631-638) is not used "
+                                      "by any reference entry point and is not implemented")
+        assert cfg_coef >= 1.0, cfg_coef
+        cfg = self.cfg
+        K = cfg.n_codebooks
+        U = len(xs)
+        assert U == len(ys) == len(mask_intervals) and U > 0
+        dev = torch.device(device) if device is not None else self._device
+        if self._device is None:
+            self.to(dev if dev is not None and dev.type == "cuda" else "cuda")
+        rpu = 2 if aug_text else 1
+        preps, rows_text, x_lens = [], [], []
+        for i in range(U):
+            x = xs[i].detach().to("cpu", torch.int64).reshape(-1)
+            yk = ys[i].detach().to("cpu", torch.int64)
+            assert yk.ndim == 2 and yk.shape[1] == K, yk.shape
+            y = yk.T.contiguous().numpy()                                    # [K, T]
+            mi = torch.as_tensor(mask_intervals[i]).detach().to("cpu", torch.int64).reshape(-1, 2)
+            context_len = int(sum(int(b) - int(a) for a, b in mi.tolist()))
+            use_ctx = bool(aug_context and context_len < 2 * 50)             # ssr.py:564-568
+            out_len = 0
+            if use_ctx:
+                p = prompts[i].detach().to("cpu", torch.int64).T.contiguous().numpy()
+                px = prompt_xs[i].detach().to("cpu", torch.int64).reshape(-1)
+                out_len = p.shape[1]
+                y = np.concatenate([p, y], axis=1)                           # ssr.py:581,591
+                x = torch.cat([px, x], 0)                                    # ssr.py:583,592
+            prep = seq.prepare(cfg, y, mi.tolist(), out_len=out_len)
+            preps.append(prep)
+            x_lens.append(int(x.shape[0]))
+            rows_text.append(x)
+            if aug_text:
+                if uncond_xs is not None:
+                    ux = uncond_xs[i].detach().to("cpu", torch.int64).reshape(-1)
+                else:   # same draw as the reference: global CPU generator (ssr.py:574)
+                    ux = torch.randint(0, self.n_text_tokens, (1, x.shape[0]))[0]
+                assert ux.shape[0] == x.shape[0]
+                rows_text.append(ux)
+        R = U * rpu
+        Lmax = max(x_lens)
+        Pmax = max(p.prompt_tokens.shape[1] for p in preps)
+        steps = max(self._max_steps(x_lens[i], preps[i].prompt_tokens.shape[1], preps[i].num_spans) for i in range(U))
+        s0s = [x_lens[i] + preps[i].prompt_tokens.shape[1] + 1 for i in range(U)]
+        total_prefill = sum(s0s) * rpu
+        self._ensure_engine(R, max(s0s) + steps + 8, max(max(s0s), min(total_prefill, 16384)), steps)
+        lib = _lib.load()
+        text = np.zeros((R, Lmax), dtype=np.int32)
+        for r, t in enumerate(rows_text):
+            text[r, :t.shape[0]] = t.numpy()
+        prom = np.zeros((U, K, max(Pmax, 1)), dtype=np.int32)
+        for i, p in enumerate(preps):
+            prom[i, :, :p.prompt_tokens.shape[1]] = p.prompt_tokens
+        tl = np.asarray(x_lens, dtype=np.int32)
+        pl = np.asarray([p.prompt_tokens.shape[1] for p in preps], dtype=np.int32)
+        ns = np.asarray([p.num_spans for p in preps], dtype=np.int32)
+        i32p = C.POINTER(C.c_int32)
+        batch = _lib.LMBatch(n_utt=U, text=text.ctypes.data_as(i32p), text_stride=Lmax, text_len=tl.ctypes.data_as(i32p),
+                             prompt=prom.ctypes.data_as(i32p), prompt_stride=prom.shape[2],
+                             prompt_len=pl.ctypes.data_as(i32p), n_spans=ns.ctypes.data_as(i32p))
+        sil = list(silence_tokens)[:_lib.MAX_SILENCE]
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item()) if noise is None else 0
+        sp = _lib.Sampling(top_k=int(top_k), top_p=float(top_p), temperature=float(temperature),
+                           stop_repetition=int(stop_repetition), n_silence=len(sil),
+                           silence_tokens=(C.c_int * _lib.MAX_SILENCE)(*(sil + [0] * (_lib.MAX_SILENCE - len(sil)))),
+                           cfg_coef=float(cfg_coef), cfg_stride=int(cfg_stride), aug_text=int(bool(aug_text)), seed=seed)
+        noise_dev = None
+        if noise is not None:   # [n_steps, U, K, V] (or [n_steps, K, V] for one utterance); padded to max_steps
+            nz = noise.detach().to(torch.float32)
+            if nz.ndim == 3:
+                nz = nz[:, None]
+            assert nz.shape[1:] == (U, K, cfg.n_audio_tokens), nz.shape
+            full = torch.ones(self._cap[3], U, K, cfg.n_audio_tokens, dtype=torch.float32)
+            full[:min(nz.shape[0], self._cap[3])] = nz[:self._cap[3]]
+            noise_dev = full.to(self._device).contiguous()
+        with torch.cuda.device(self._device):
+            st = _lib.stream_ptr()
+            ev0, ev1, ev2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            ev0.record()
+            _lib.check(lib.ssrb_lm_begin(self._h, C.byref(batch), C.byref(sp),
+                                         C.c_void_p(noise_dev.data_ptr()) if noise_dev is not None else None, st), "ssrb_lm_begin")
+            ev1.record()
+            nd, it = C.c_int(0), C.c_int(0)
+            done = 0
+            while True:
+                _lib.check(lib.ssrb_lm_poll(self._h, st, C.byref(nd), C.byref(it)), "ssrb_lm_poll")
+                done = nd.value
+                if done >= U or it.value >= self._cap[3] + 1:
+                    break
+                _lib.check(lib.ssrb_lm_decode(self._h, int(poll_every), st), "ssrb_lm_decode")
+            ev2.record()
+            torch.cuda.synchronize()
+            self.last_stats = {"prefill_ms": ev0.elapsed_time(ev1), "decode_ms": ev1.elapsed_time(ev2), "iterations": it.value}
+            results = []
+            buf = np.zeros((self._cap[3], K), dtype=np.int32)
+            span_len = (C.c_int32 * _lib.MAX_SPANS)()
+            n_tok = C.c_int(0)
+            for i in range(U):
+                _lib.check(lib.ssrb_lm_read_tokens(self._h, st, i, C.c_void_p(buf.ctypes.data), buf.shape[0],
+                                                   C.byref(n_tok), span_len), "ssrb_lm_read_tokens")
+                toks = buf[:n_tok.value].astype(np.int64)
+                spans, o = [], 0
+                for s in range(preps[i].num_spans):
+                    spans.append(toks[o:o + span_len[s]])
+                    o += span_len[s]
+                res, marks, masks, nmi = seq.finalize(cfg, preps[i], spans)
+                results.append((torch.from_numpy(res).unsqueeze(0).to(dev if dev is not None else self._device),
+                                torch.from_numpy(marks).unsqueeze(0), masks, nmi))
+        return results
+
+    # ---- test hooks -------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def teacher_forced_logits(self, x: torch.Tensor, audio_tokens: torch.Tensor) -> torch.Tensor:
+        """x [Lx], audio_tokens [K, Ty] -> fp32 logits [Ty, K, V] (CPU) via the prefill path."""
+        K, V = self.cfg.n_codebooks, self.cfg.n_audio_tokens
+        Lx, Ty = int(x.shape[0]), int(audio_tokens.shape[1])
+        if self._device is None:
+            self.to("cuda")
+        self._ensure_engine(2, Lx + Ty + 16, Lx + Ty + 16, 8)
+        xt = x.detach().to("cpu", torch.int32).contiguous().numpy()
+        at = audio_tokens.detach().to("cpu", torch.int32).contiguous().numpy()
+        out = np.zeros((Ty, K, V), dtype=np.float32)
+        with torch.cuda.device(self._device):
+            _lib.check(_lib.load().ssrb_lm_teacher_forced(self._h, C.c_void_p(xt.ctypes.data), Lx, C.c_void_p(at.ctypes.data),
+                                                          Ty, C.c_void_p(out.ctypes.data), _lib.stream_ptr()), "teacher_forced")
+        return torch.from_numpy(out)
+
+    def last_raw_logits(self) -> torch.Tensor:
+        """[R, K, V] fp32 head outputs of the most recent iteration (before CFG / rules)."""
+        K, V = self.cfg.n_codebooks, self.cfg.n_audio_tokens
+        out = np.zeros((self._cap[0], K, V), dtype=np.float32)
+        with torch.cuda.device(self._device):
+            _lib.check(_lib.load().ssrb_lm_read_logits(self._h, _lib.stream_ptr(), C.c_void_p(out.ctypes.data)), "read_logits")
+        return torch.from_numpy(out)
+
+    def step_bytes(self):
+        wb, kb = C.c_double(0), C.c_double(0)
+        with torch.cuda.device(self._device):
+            _lib.check(_lib.load().ssrb_lm_step_bytes(self._h, _lib.stream_ptr(), C.byref(wb), C.byref(kb)), "step_bytes")
+        return wb.value, kb.value

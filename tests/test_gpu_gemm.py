@@ -1,0 +1,65 @@
+"""GEMM kernels behind ssrb_op_gemm vs a plain torch fp32 reference of the same op."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from ssr_speech_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+
+def run_gemm(A, W, bias, res, act, dtype, impl):
+    lib = _lib.load()
+    M, K = A.shape
+    N = W.shape[0]
+    out = torch.empty(M, N, dtype=torch.float32, device="cuda")
+    _lib.check(lib.ssrb_op_gemm(C.c_void_p(A.data_ptr()), C.c_void_p(W.data_ptr()),
+                                C.c_void_p(bias.data_ptr()) if bias is not None else None,
+                                C.c_void_p(res.data_ptr()) if res is not None else None, C.c_void_p(out.data_ptr()),
+                                M, N, K, dtype, act, impl, _lib.stream_ptr()), "op_gemm")
+    torch.cuda.synchronize()
+    return out
+
+
+def ref_gemm(A, W, bias, res, act):
+    y = A.float() @ W.float().t()
+    if bias is not None:
+        y = y + bias
+    if act == 1:
+        y = torch.relu(y)
+    elif act == 2:
+        y = torch.nn.functional.gelu(y)
+    if res is not None:
+        y = y + res
+    return y
+
+
+SHAPES = [(1, 768, 256), (2, 2056, 1024), (3, 6144, 2048), (7, 72, 32), (64, 2048, 2048), (200, 6144, 2048), (611, 8192, 2048),
+          (130, 2056, 1024), (64, 2048, 8192)]
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+@pytest.mark.parametrize("act", [0, 1, 2])
+def test_simt_fp32(M, N, K, act):
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    W = torch.randn(N, K, device="cuda", generator=g) / K ** 0.5
+    b = torch.randn(N, device="cuda", generator=g)
+    r = torch.randn(M, N, device="cuda", generator=g)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    got = run_gemm(A, W, b, r, act, _lib.SSRB_DTYPE_F32, 1)
+    want = ref_gemm(A.double(), W.double(), b.double(), r.double(), act).float() if False else ref_gemm(A, W, b, r, act)
+    assert (got - want).abs().max().item() <= 2e-4
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_simt_bf16(M, N, K):
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
+    b = torch.randn(N, device="cuda", generator=g)
+    got = run_gemm(A, W, b, None, 1, _lib.SSRB_DTYPE_BF16, 1)
+    want = ref_gemm(A, W, b, None, 1)
+    assert (got - want).abs().max().item() <= 2e-3

@@ -1,0 +1,100 @@
+"""Host-side (integer) logic: sequence surgery, config parsing, sharding, padding/length formulas."""
+import math
+from argparse import Namespace
+
+import numpy as np
+import pytest
+import torch
+
+from ssr_speech_b200 import seq
+from ssr_speech_b200.config import CodecConfig, SSRConfig, cfg_830m, cfg_tiny
+from ssr_speech_b200.dist import shard_range
+
+
+def test_config_from_reference_namespace():
+    cfg = cfg_830m()
+    ns = cfg.to_namespace()
+    assert isinstance(ns.audio_vocab_size, str)           # e830M.sh passes a string that ssr.py evals
+    back = SSRConfig.from_args(ns)
+    assert back == cfg and back.n_audio_tokens == 2056 and back.n_text_tokens == 101 and back.ffn_dim == 8192
+
+
+def test_config_asserts_like_reference():
+    ns = cfg_830m().to_namespace()
+    ns.eog = 7
+    with pytest.raises(AssertionError):
+        SSRConfig.from_args(ns)
+
+
+@pytest.mark.parametrize("n", [0, 1, 5, 17])
+def test_delay_pattern_roundtrip(n):
+    cfg = cfg_tiny()
+    rng = np.random.default_rng(n)
+    t = rng.integers(0, cfg.audio_vocab_size, (4, n))
+    d = seq.delay_pattern(t, cfg.empty_token)
+    assert d.shape == (4, n + 3)
+    for q in range(4):
+        assert (d[q, :q] == cfg.empty_token).all() and (d[q, q + n:] == cfg.empty_token).all()
+    assert np.array_equal(seq.revert_delay_pattern(d, cfg.empty_token), t)
+
+
+def test_prepare_tts_layout():
+    cfg = cfg_tiny()
+    T = 12
+    y = np.arange(4 * T).reshape(4, T) % cfg.audio_vocab_size
+    p = seq.prepare(cfg, y, [[T, T]])
+    # sos + T frames delayed (T+1+3), <mts0>, [eos] delayed (4)  -> Y0-1 = T + 9 (Y0 = T + 10)
+    assert p.prompt_tokens.shape == (4, T + 9)
+    assert (p.prompt_tokens[:, T + 4] == cfg.mts).all()
+    assert p.prompt_tokens[0, 0] == cfg.sos and p.prompt_tokens[0, T + 5] == cfg.eos
+    assert p.non_mask_intervals == [(0, T), (T, T)] and p.num_spans == 1
+
+
+def test_prepare_edit_two_spans_and_finalize_shapes():
+    cfg = cfg_tiny()
+    T = 30
+    rng = np.random.default_rng(0)
+    y = rng.integers(0, cfg.audio_vocab_size, (4, T))
+    p = seq.prepare(cfg, y, [[5, 9], [20, 28]])
+    assert p.num_spans == 2 and p.non_mask_intervals == [(0, 5), (9, 20), (28, 30)]
+    # generated spans: n tokens + eog column, delayed -> n + 4 iterations
+    spans = []
+    for n in (3, 6):
+        g = rng.integers(0, cfg.audio_vocab_size, (4, n))
+        g = np.concatenate([g, np.full((4, 1), cfg.eog)], 1)
+        spans.append(seq.delay_pattern(g, cfg.empty_token).T)
+    res, marks, masks, nmi = seq.finalize(cfg, p, spans)
+    assert res.shape == (4, 5 + 3 + 11 + 6 + 2)
+    assert marks.sum() == 9 and masks == [(0, 5), (8, 19), (25, 27)]
+    assert np.array_equal(res[:, :5], y[:, :5]) and np.array_equal(res[:, -2:], y[:, 28:])
+
+
+def test_expected_steps_matches_survey():
+    cfg = cfg_830m()
+    # T=150, Lx=60 -> 441 generated frames, 445 iterations
+    assert seq.expected_steps(cfg, 60, 150 + 9) == 445
+    assert seq.expected_steps(cfg, 40, 150 + 9) == 245
+
+
+def test_shard_range_partition():
+    for n in (0, 1, 7, 256):
+        for w in (1, 2, 3, 8):
+            spans = [shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
+
+
+# length formulas the reference's own tests pin (audiocraft/tests/modules/test_conv.py:151-203)
+@pytest.mark.parametrize("k,s", [(4, 1), (4, 2), (10, 5), (7, 1), (16, 8), (8, 4)])
+@pytest.mark.parametrize("T", [10, 23, 320, 1001])
+def test_conv_and_convtr_length_rules(k, s, T):
+    from codec_oracle import CodecOracle
+    sd = {"c.weight": torch.randn(3, 2, k), "c.bias": torch.zeros(3), "t.weight": torch.randn(2, 3, k), "t.bias": torch.zeros(3)}
+    o = CodecOracle(CodecConfig(), sd)
+    x = torch.randn(1, 2, T)
+    y = o.conv(x, "c.", s)
+    assert y.shape[-1] == math.ceil(T / s)
+    if k == 2 * s:
+        z = o.convtr(x, "t.", s)
+        assert z.shape[-1] == T * s

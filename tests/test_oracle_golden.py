@@ -1,0 +1,99 @@
+"""CPU: the oracle restatement reproduces the golden vectors recorded from the UNMODIFIED reference
+(oracle/gen_golden.py).  This is what pins the oracle (the reference ships no golden vectors)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from codec_oracle import CodecOracle
+from lm_oracle import LMOracle
+from ssr_speech_b200 import seq
+from ssr_speech_b200.config import CodecConfig, cfg_tiny
+from ssr_speech_b200.synth import make_codec_state_dict, make_lm_state_dict
+
+LM_CASES = ["tts_greedy", "edit_cfg_sampled", "edit2_cfg_greedy", "tts_cfg_temp_topk", "edit_head_nokv"]
+
+
+@pytest.fixture(scope="module")
+def lm_oracle():
+    cfg = cfg_tiny()
+    return cfg, LMOracle(cfg, make_lm_state_dict(cfg, seed=7))
+
+
+@pytest.mark.parametrize("name", LM_CASES)
+def test_lm_oracle_reproduces_reference_tokens(lm_oracle, gold_dir, name):
+    cfg, oracle = lm_oracle
+    g = np.load(os.path.join(gold_dir, f"lm_{name}.npz"))
+    kw = json.loads(str(g["kw"]))
+    kw.pop("kvcache")
+    prep = seq.prepare(cfg, g["y"].T.copy(), g["mask_interval"].tolist())
+    uncond = torch.from_numpy(g["uncond_x"]) if kw["aug_text"] else None
+    trace = []
+    spans = oracle.inference(torch.from_numpy(g["x"]), torch.from_numpy(prep.prompt_tokens), prep.num_spans,
+                             silence_tokens=g["silence"].tolist(), uncond_x=uncond, noise=torch.from_numpy(g["noise"]),
+                             trace=trace, **kw)
+    assert [len(s) for s in spans] == g["ref_span_lens"].tolist()
+    assert np.array_equal(np.concatenate(spans, 0), g["ref_span_tokens"])
+    res, marks, masks, nmi = seq.finalize(cfg, prep, spans)
+    assert np.array_equal(res, g["ref_res"]) and np.array_equal(marks, g["ref_marks"])
+    assert np.array_equal(np.asarray(masks), g["ref_masks"]) and np.array_equal(np.asarray(nmi), g["ref_nmi"])
+    np.testing.assert_allclose(trace[0].raw_logits.numpy(), g["raw_logits_step0"], atol=2e-5)
+
+
+def test_lm_oracle_teacher_forced_logits(lm_oracle, gold_dir):
+    cfg, oracle = lm_oracle
+    g = np.load(os.path.join(gold_dir, "lm_teacher_forced.npz"))
+    lg = oracle.teacher_forced_logits(torch.from_numpy(g["x"]), torch.from_numpy(g["toks"]))
+    np.testing.assert_allclose(lg.numpy(), g["ref_logits"], atol=2e-5)
+
+
+def test_lm_oracle_incremental_equals_full(lm_oracle, gold_dir):
+    """kvcache=1 and kvcache=0 give identical tokens under greedy (SURVEY §4 property i)."""
+    cfg, oracle = lm_oracle
+    g = np.load(os.path.join(gold_dir, "lm_tts_greedy.npz"))
+    kw = json.loads(str(g["kw"]))
+    kw.pop("kvcache")
+    prep = seq.prepare(cfg, g["y"].T.copy(), g["mask_interval"].tolist())
+    a = oracle.inference(torch.from_numpy(g["x"]), torch.from_numpy(prep.prompt_tokens), 1, incremental=True, max_steps=12, **kw)
+    b = oracle.inference(torch.from_numpy(g["x"]), torch.from_numpy(prep.prompt_tokens), 1, incremental=False, max_steps=12, **kw)
+    assert np.array_equal(a[0], b[0])
+
+
+@pytest.fixture(scope="module")
+def codec_oracle(gold_dir):
+    g = np.load(os.path.join(gold_dir, "codec_small.npz"))
+    cfg = CodecConfig()
+    sd = make_codec_state_dict(cfg, seed=int(g["weights_seed"]), codebook_mu=g["codebook_mu"], codebook_sigma=g["codebook_sigma"])
+    return cfg, CodecOracle(cfg, sd), g
+
+
+def test_codec_oracle_encode(codec_oracle):
+    cfg, o, g = codec_oracle
+    codes, _, emb = o.encode(torch.from_numpy(g["wav"]))
+    np.testing.assert_allclose(emb.numpy(), g["ref_emb"], atol=1e-6)
+    assert np.array_equal(codes.numpy(), g["ref_codes"])
+    assert np.array_equal(o.rvq_encode(torch.from_numpy(g["ref_emb"])).numpy(), g["ref_codes"])
+
+
+def test_codec_oracle_decode_and_wmdecode(codec_oracle):
+    cfg, o, g = codec_oracle
+    codes = torch.from_numpy(g["ref_codes"])
+    np.testing.assert_allclose(o.decode(codes).numpy(), g["ref_dec"], atol=1e-6)
+    wm, ml = o.wmdecode(codes, torch.from_numpy(g["marks"]), torch.from_numpy(g["wav"]))
+    np.testing.assert_allclose(wm.numpy(), g["ref_wm"], atol=2e-6)
+    np.testing.assert_allclose(ml.numpy(), g["ref_mark_logits"], atol=2e-6)
+
+
+def test_codec_oracle_demo_wav_roundtrip(gold_dir):
+    """BASELINE config 1 (first 2 s of demo/84_121550_000074_000000.wav): encode -> RVQ -> decode."""
+    g = np.load(os.path.join(gold_dir, "codec_demo2s.npz"))
+    cfg = CodecConfig()
+    sd = make_codec_state_dict(cfg, seed=int(g["weights_seed"]), codebook_mu=g["codebook_mu"], codebook_sigma=g["codebook_sigma"])
+    o = CodecOracle(cfg, sd)
+    codes, _, emb = o.encode(torch.from_numpy(g["wav"]))
+    assert codes.shape == (1, 4, 100)
+    np.testing.assert_allclose(emb.numpy(), g["ref_emb"], atol=1e-6)
+    assert np.array_equal(codes.numpy(), g["ref_codes"])
+    np.testing.assert_allclose(o.decode(codes).numpy(), g["ref_dec"], atol=1e-6)
