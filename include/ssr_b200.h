@@ -130,6 +130,12 @@ int ssrb_lm_teacher_forced(ssrb_lm* lm, const int32_t* text, int Lx, const int32
  * weights streamed once + KV read for every active row + KV written.  Synchronises. */
 int ssrb_lm_step_bytes(ssrb_lm* lm, void* stream, double* weight_bytes, double* kv_bytes);
 
+/* Profiling hook (bench.py roofline): runs `n_steps` decode iterations WITHOUT the CUDA graph, with CUDA
+ * events (on `stream`) around every kernel class, and returns the average milliseconds per iteration spent in
+ * ms_by_class[4] = {attention, GEMMs, layernorm/embed/kv-append, sampling} and in total.  The iterations are
+ * real (they advance the batch state).  Synchronises. */
+int ssrb_lm_profile_steps(ssrb_lm* lm, int n_steps, void* stream, double* ms_by_class, double* total_ms);
+
 /* ------------------------------------------------------------------------------------------------
  * WM-Encodec  —  replaces audiocraft/models/wmencodec.py::WMEncodecModel.{encode,decode,wmdecode}
  * and below it audiocraft/modules/{seanet,conv,lstm}.py, audiocraft/quantization/{vq,core_vq}.py.

@@ -1,7 +1,404 @@
-// placeholder until the tcgen05 kernel lands
+// gemm_tc.cu — bf16 GEMM on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM, operands
+// staged by TMA into 128B-swizzled shared memory, mbarrier producer/consumer pipeline).  sm_100a only.
+//
+//   C[M,N] = act(A[M,K] . W[N,K]^T + bias) (+ residual)         A, W bf16 K-major; fp32 accumulate
+//
+// Replaces the F.linear call sites of the decoder layer / heads in production (bf16) mode:
+// models/modules/activation.py:86 (QKV), :637 (out_proj), models/modules/transformer.py:386-388 (FFN),
+// models/ssr.py:175-179,688 (heads).
+//
+// Two shapes of the same pipeline:
+//   SWAP  (decode, M <= 128 rows): the WEIGHT tile is the 128-row MMA "A" operand, the activations are the
+//         MMA "B" operand (N = rows padded to 16/32/64/128).  The step is HBM-bound on the weight stream, so
+//         the grid is (N/128 tiles) x split-K slices sized to put >= 2 CTAs on every SM; fp32 partials go to
+//         an L2-resident workspace and the last-arriving CTA of a tile reduces them in a fixed order
+//         (deterministic) and applies the epilogue.
+//   FLAT  (prefill, large M): activations are the 128-row operand, a 128-wide weight tile is the N operand.
+//
+// warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue.
+#include <cuda.h>
+
+#include <map>
+#include <mutex>
+#include <tuple>
+
 #include "common.cuh"
+#include "../../include/ssr_b200.h"
+
 namespace ssrb {
-bool gemm_tc_supported(const GemmArgs&) { return false; }
-size_t gemm_tc_workspace_bytes(int, int) { return 0; }
-int gemm_tc(const GemmArgs&, void*, size_t, cudaStream_t) { set_error("tcgen05 GEMM not built"); return 1; }
+
+namespace {
+
+constexpr int BK = 64;                 // bf16 elements per k-block = one 128-byte swizzle row
+constexpr int P_ROWS = 128;            // MMA M
+constexpr int P_BYTES = P_ROWS * BK * 2;
+constexpr int MAX_GROUPS = 4;
+
+struct TmaPair { CUtensorMap p, q; };
+struct TmaGroup { TmaPair g[MAX_GROUPS]; };
+
+struct TcParams {
+    int M, N, K, nkb, splits, kb_per_split;
+    const float* bias; long long bias_gs;
+    const float* residual; long long ldr;
+    void* C; long long ldc, c_gs; int c_dtype;
+    int act;
+    float* ws; int* tickets; int Mpad;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"((unsigned long long)map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
+// start>>4 | LBO(ignored for swizzled K-major)=1 <<16 | SBO = 1024 B (8 rows x 128 B) >>4 <<32 | version 1 <<46 | layout 2 <<61
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+                 ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    if (act == ACT_RELU) return fmaxf(v, 0.f);
+    if (act == ACT_GELU) return gelu_erf(v);
+    return v;
+}
+
+template <int QROWS> struct TcCfg {
+    static constexpr int Q_BYTES = QROWS * BK * 2;
+    static constexpr int STAGE_BYTES = P_BYTES + Q_BYTES;
+    static constexpr int STAGES = QROWS >= 128 ? 3 : 4;
+    static constexpr int TMEM_COLS = QROWS < 32 ? 32 : QROWS;
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int QROWS, bool SWAP>
+__global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ TmaGroup maps, const TcParams prm) {
+    using Cfg = TcCfg<QROWS>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B tiles need 1024 B alignment
+    const uint32_t bar_base = base + Cfg::STAGES * Cfg::STAGE_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
+    const uint32_t accum_bar = bar_base + 8u * (2 * Cfg::STAGES);
+    const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 1);
+    __shared__ int s_last;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = blockIdx.z;
+    // tile coordinates
+    int p_row0, q_row0, kb0, kb1, split = 0;
+    if (SWAP) {
+        p_row0 = blockIdx.x * P_ROWS;            // output feature n0
+        q_row0 = 0;                              // activation rows 0..QROWS
+        split = blockIdx.y;
+        kb0 = split * prm.kb_per_split;
+        kb1 = min(prm.nkb, kb0 + prm.kb_per_split);
+    } else {
+        q_row0 = blockIdx.x * QROWS;             // n0
+        p_row0 = blockIdx.y * P_ROWS;            // m0
+        kb0 = 0; kb1 = prm.nkb;
+    }
+    const int nk = kb1 - kb0;
+    const CUtensorMap* mapP = &maps.g[grp].p;
+    const CUtensorMap* mapQ = &maps.g[grp].q;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < Cfg::STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            for (int i = 0; i < nk; i++) {
+                const int s = i % Cfg::STAGES;
+                const uint32_t ph = (i / Cfg::STAGES) & 1;
+                mbar_wait(empty_bar(s), ph ^ 1);
+                mbar_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
+                const uint32_t sp = base + s * Cfg::STAGE_BYTES;
+                tma_load_2d(sp, mapP, full_bar(s), (kb0 + i) * BK, p_row0);
+                tma_load_2d(sp + P_BYTES, mapQ, full_bar(s), (kb0 + i) * BK, q_row0);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): c=f32 (1<<4), a=b=bf16 (1<<7,1<<10),
+            // K-major both, N>>3 at bit 17, M>>4 at bit 24
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(QROWS >> 3) << 17) | ((uint32_t)(P_ROWS >> 4) << 24);
+            for (int i = 0; i < nk; i++) {
+                const int s = i % Cfg::STAGES;
+                const uint32_t ph = (i / Cfg::STAGES) & 1;
+                mbar_wait(full_bar(s), ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sp = base + s * Cfg::STAGE_BYTES;
+                const uint64_t da = make_desc(sp), db = make_desc(sp + P_BYTES);
+#pragma unroll
+                for (int k = 0; k < BK / 16; k++)
+                    umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);   // +32 B per K=16
+                umma_commit(empty_bar(s));
+            }
+            umma_commit(accum_bar);
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers -> global =====
+        const int lg = warp & 3;                         // TMEM lane group this warp may access
+        const int prow = p_row0 + lg * 32 + lane;        // row of the 128-row operand this thread owns
+        const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16);
+        const int et = threadIdx.x - 64;                 // 0..127
+        if (nk > 0) {
+            mbar_wait(accum_bar, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        if (SWAP) {
+            const int n = prow;
+            const bool nok = n < prm.N;
+            const float bv = (prm.bias && nok) ? prm.bias[grp * prm.bias_gs + n] : 0.f;
+            auto finish = [&](int r, float v) {
+                v = apply_act(v + bv, prm.act);
+                if (prm.residual) v += prm.residual[(long long)r * prm.ldr + n];
+                const long long o = grp * prm.c_gs + (long long)r * prm.ldc + n;
+                if (prm.c_dtype == SSRB_DTYPE_F32) reinterpret_cast<float*>(prm.C)[o] = v;
+                else reinterpret_cast<bf16*>(prm.C)[o] = __float2bfloat16_rn(v);
+            };
+            float* wsg = prm.ws + (size_t)grp * prm.splits * prm.Mpad * prm.N;
+#pragma unroll 1
+            for (int c0 = 0; c0 < QROWS; c0 += 16) {
+                if (c0 >= prm.M) break;
+                float v[16];
+                if (nk > 0) tmem_ld16(taddr + c0, v);
+                else {
+#pragma unroll
+                    for (int j = 0; j < 16; j++) v[j] = 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    const int r = c0 + j;
+                    if (r < prm.M && nok) {
+                        if (prm.splits == 1) finish(r, v[j]);
+                        else wsg[((size_t)split * prm.Mpad + r) * prm.N + n] = v[j];
+                    }
+                }
+            }
+            if (prm.splits > 1) {
+                __threadfence();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const int tile = grp * gridDim.x + blockIdx.x;
+                if (et == 0) {
+                    const int t = atomicAdd(&prm.tickets[tile], 1);
+                    s_last = (t == prm.splits - 1);
+                    if (s_last) prm.tickets[tile] = 0;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (s_last && nok) {
+                    __threadfence();
+                    for (int r = 0; r < prm.M; r++) {
+                        float acc = 0.f;
+                        for (int s = 0; s < prm.splits; s++) acc += __ldcg(wsg + ((size_t)s * prm.Mpad + r) * prm.N + n);
+                        finish(r, acc);
+                    }
+                }
+            }
+        } else {
+            const int m = prow;
+            const bool mok = m < prm.M;
+#pragma unroll 1
+            for (int c0 = 0; c0 < QROWS; c0 += 16) {
+                float v[16];
+                tmem_ld16(taddr + c0, v);
+                const int n0 = q_row0 + c0;
+                if (!mok || n0 >= prm.N) continue;
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    const int n = n0 + j;
+                    float x = v[j] + ((prm.bias && n < prm.N) ? prm.bias[n] : 0.f);
+                    x = apply_act(x, prm.act);
+                    if (prm.residual && n < prm.N) x += prm.residual[(long long)m * prm.ldr + n];
+                    v[j] = x;
+                }
+                if (n0 + 16 <= prm.N) {
+                    if (prm.c_dtype == SSRB_DTYPE_F32) {
+                        float* cp = reinterpret_cast<float*>(prm.C) + (long long)m * prm.ldc + n0;
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    } else {
+                        bf16* cp = reinterpret_cast<bf16*>(prm.C) + (long long)m * prm.ldc + n0;
+                        float lo[8], hi[8];
+#pragma unroll
+                        for (int j = 0; j < 8; j++) { lo[j] = v[j]; hi[j] = v[8 + j]; }
+                        store8(cp, lo);
+                        store8(cp + 8, hi);
+                    }
+                } else {
+                    for (int j = 0; j < 16 && n0 + j < prm.N; j++) {
+                        const long long o = (long long)m * prm.ldc + n0 + j;
+                        if (prm.c_dtype == SSRB_DTYPE_F32) reinterpret_cast<float*>(prm.C)[o] = v[j];
+                        else reinterpret_cast<bf16*>(prm.C)[o] = __float2bfloat16_rn(v[j]);
+                    }
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    });
+    return fn;
+}
+
+// 2-D bf16 row-major [rows, cols] with leading dimension ld (elements); box = 64 cols x box_rows, 128B swizzle
+int make_map(CUtensorMap* m, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    SSRB_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
+    SSRB_CHECK(((uintptr_t)ptr & 15) == 0 && (ld * 2) % 16 == 0, "TMA operand must be 16-byte aligned");
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SSRB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed");
+    return 0;
+}
+
+int qrows_for(int M) { return M <= 16 ? 16 : (M <= 32 ? 32 : (M <= 64 ? 64 : 128)); }
+
+int pick_splits(int tiles, int nkb) {
+    int s = 1;
+    while (s * 2 <= nkb / 4 && tiles * s < 296) s *= 2;     // >= 4 k-blocks per CTA, aim for >= 2 CTAs per SM
+    return s;
+}
+
+template <int QROWS, bool SWAP>
+int launch_tc(const TmaGroup& maps, const TcParams& prm, dim3 grid, cudaStream_t s) {
+    using Cfg = TcCfg<QROWS>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        SSRB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<QROWS, SWAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        attr_done = true;
+    }
+    SSRB_LAUNCH((gemm_tc_kernel<QROWS, SWAP>), grid, 192, Cfg::SMEM, s, maps, prm);
+    return 0;
+}
+
+}  // namespace
+
+bool gemm_tc_supported(const GemmArgs& g) {
+    if (g.ab_dtype != SSRB_DTYPE_BF16) return false;
+    if (g.K % BK != 0 || g.K < BK) return false;
+    if (g.lda % 8 != 0 || g.ldw % 8 != 0) return false;
+    if (g.groups > MAX_GROUPS) return false;
+    if (g.groups > 1 && g.M > 128) return false;
+    if ((g.a_gs % 8) != 0 || (g.w_gs % 8) != 0) return false;
+    return g.M > 0 && g.N > 0;
+}
+
+size_t gemm_tc_workspace_bytes(int max_rows_decode, int max_n) {
+    // split-K partials: splits(<=32) x Mpad x N x groups(folded into N budget) + tickets
+    const size_t mpad = (size_t)(max_rows_decode <= 128 ? qrows_for(max_rows_decode) : 128);
+    return (size_t)32 * mpad * (size_t)max_n * 4 + 65536;
+}
+
+int gemm_tc(const GemmArgs& g, void* workspace, size_t workspace_bytes, cudaStream_t s) {
+    SSRB_CHECK(gemm_tc_supported(g), "gemm_tc: unsupported problem");
+    TmaGroup maps;
+    memset(&maps, 0, sizeof(maps));
+    TcParams prm{};
+    prm.M = g.M; prm.N = g.N; prm.K = g.K; prm.nkb = g.K / BK;
+    prm.bias = g.bias; prm.bias_gs = g.bias_gs; prm.residual = g.residual; prm.ldr = g.ldr;
+    prm.C = g.C; prm.ldc = g.ldc; prm.c_gs = g.c_gs; prm.c_dtype = g.c_dtype; prm.act = g.act;
+    const bf16* A = reinterpret_cast<const bf16*>(g.A);
+    const bf16* W = reinterpret_cast<const bf16*>(g.W);
+    if (g.M <= 128) {
+        const int q = qrows_for(g.M);
+        const int tiles = cdiv(g.N, P_ROWS);
+        prm.splits = pick_splits(tiles * g.groups, prm.nkb);
+        prm.kb_per_split = cdiv(prm.nkb, prm.splits);
+        prm.Mpad = q;
+        const size_t ws_need = (size_t)g.groups * prm.splits * q * g.N * 4;
+        const size_t tick_off = (workspace_bytes >= 65536) ? workspace_bytes - 65536 : 0;
+        if (prm.splits > 1) {
+            SSRB_CHECK(workspace && ws_need <= tick_off && (size_t)tiles * g.groups * 4 <= 65536, "gemm_tc: split-K workspace too small");
+            prm.ws = reinterpret_cast<float*>(workspace);
+            prm.tickets = reinterpret_cast<int*>(reinterpret_cast<char*>(workspace) + tick_off);
+        }
+        for (int i = 0; i < g.groups; i++) {
+            SSRB_TRY(make_map(&maps.g[i].p, W + i * g.w_gs, g.N, g.K, g.ldw, P_ROWS));
+            SSRB_TRY(make_map(&maps.g[i].q, A + i * g.a_gs, g.M, g.K, g.lda, q));
+        }
+        dim3 grid(tiles, prm.splits, g.groups);
+        switch (q) {
+            case 16: return launch_tc<16, true>(maps, prm, grid, s);
+            case 32: return launch_tc<32, true>(maps, prm, grid, s);
+            case 64: return launch_tc<64, true>(maps, prm, grid, s);
+            default: return launch_tc<128, true>(maps, prm, grid, s);
+        }
+    }
+    prm.splits = 1; prm.kb_per_split = prm.nkb; prm.Mpad = 0;
+    SSRB_TRY(make_map(&maps.g[0].p, A, g.M, g.K, g.lda, P_ROWS));
+    SSRB_TRY(make_map(&maps.g[0].q, W, g.N, g.K, g.ldw, 128));
+    dim3 grid(cdiv(g.N, 128), cdiv(g.M, P_ROWS), 1);
+    return launch_tc<128, false>(maps, prm, grid, s);
+}
+
+}  // namespace ssrb

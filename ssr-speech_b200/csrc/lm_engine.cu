@@ -8,6 +8,7 @@
 // and replayed as a CUDA graph, with no host synchronisation inside the loop.
 #include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "lm_kernels.cuh"
@@ -66,6 +67,19 @@ struct ssrb_lm {
     const float* noise = nullptr;
     cudaGraphExec_t graph = nullptr;
     bool use_graph = true;
+    unsigned long long graph_kernels = 0;       // kernels captured in one decode-step graph
+    // profiling (ssrb_lm_profile_steps): CUDA events around every kernel class of un-graphed steps
+    bool prof = false;
+    std::vector<std::tuple<int, cudaEvent_t, cudaEvent_t>> prof_ev;
+};
+
+enum ProfClass { PC_ATTN = 0, PC_GEMM = 1, PC_SMALL = 2, PC_SAMPLE = 3, PC_COUNT = 4 };
+struct ProfScope {
+    ssrb_lm* lm; cudaStream_t s; cudaEvent_t e0 = nullptr, e1 = nullptr; int cls;
+    ProfScope(ssrb_lm* l, int c, cudaStream_t st) : lm(l), s(st), cls(c) {
+        if (lm->prof) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, s); }
+    }
+    ~ProfScope() { if (lm->prof) { cudaEventRecord(e1, s); lm->prof_ev.emplace_back(cls, e0, e1); } }
 };
 
 static int dev_alloc(void** p, size_t bytes) {
@@ -257,6 +271,7 @@ int ssrb_lm_check_loaded(ssrb_lm* lm) {
 
 // ---- GEMM dispatch ---------------------------------------------------------------------------------
 static int gemm(ssrb_lm* lm, GemmArgs g, cudaStream_t s) {
+    ProfScope ps(lm, PC_GEMM, s);
     g.ab_dtype = lm->wdt;
     if (lm->wdt == SSRB_DTYPE_BF16 && lm->cfg.gemm_impl != 1 && gemm_tc_supported(g))
         return gemm_tc(g, lm->tc_ws, lm->tc_ws_bytes, s);
@@ -270,7 +285,7 @@ static int run_layer(ssrb_lm* lm, int n, int M, bool prefill, int n_rows, int ma
     const size_t e = lm->esz;
     void* kc = (char*)lm->kcache + (size_t)n * lm->kv_layer_elems * e;
     void* vc = (char*)lm->vcache + (size_t)n * lm->kv_layer_elems * e;
-    SSRB_TRY(launch_layernorm(lm->x, nullptr, M, D, w.ln1w, w.ln1b, lm->hn, lm->wdt, s));
+    { ProfScope ps(lm, PC_SMALL, s); SSRB_TRY(launch_layernorm(lm->x, nullptr, M, D, w.ln1w, w.ln1b, lm->hn, lm->wdt, s)); }
     GemmArgs g;
     g.A = lm->hn; g.lda = D; g.W = w.wqkv; g.ldw = D; g.bias = w.bqkv; g.C = lm->qkv; g.ldc = 3 * D;
     g.M = M; g.N = 3 * D; g.K = D; g.c_dtype = SSRB_DTYPE_F32;
@@ -280,7 +295,8 @@ static int run_layer(ssrb_lm* lm, int n, int M, bool prefill, int n_rows, int ma
         SSRB_TRY(launch_attn_prefill(lm->qkv, D, H, kc, vc, lm->wdt, lm->cfg.max_seq, n_rows, lm->d_row_ids,
                                      lm->d_row_start, lm->d_row_len, max_len, lm->ao, lm->wdt, s));
     } else {
-        SSRB_TRY(launch_kv_append(lm->qkv, M, D, H, nullptr, nullptr, lm->d_seq_len, kc, vc, lm->wdt, lm->cfg.max_seq, s));
+        { ProfScope ps(lm, PC_SMALL, s); SSRB_TRY(launch_kv_append(lm->qkv, M, D, H, nullptr, nullptr, lm->d_seq_len, kc, vc, lm->wdt, lm->cfg.max_seq, s)); }
+        ProfScope ps(lm, PC_ATTN, s);
         SSRB_TRY(launch_attn_decode(lm->qkv, M, D, H, kc, vc, lm->wdt, lm->cfg.max_seq, lm->d_seq_len, lm->d_state,
                                     lm->rpu, lm->attn_ws, lm->tickets, lm->ao, lm->wdt, s));
     }
@@ -288,7 +304,7 @@ static int run_layer(ssrb_lm* lm, int n, int M, bool prefill, int n_rows, int ma
     g.A = lm->ao; g.lda = D; g.W = w.wo; g.ldw = D; g.bias = w.bo; g.residual = lm->x; g.ldr = D; g.C = lm->x; g.ldc = D;
     g.M = M; g.N = D; g.K = D; g.c_dtype = SSRB_DTYPE_F32;
     SSRB_TRY(gemm(lm, g, s));
-    SSRB_TRY(launch_layernorm(lm->x, nullptr, M, D, w.ln2w, w.ln2b, lm->hn, lm->wdt, s));
+    { ProfScope ps(lm, PC_SMALL, s); SSRB_TRY(launch_layernorm(lm->x, nullptr, M, D, w.ln2w, w.ln2b, lm->hn, lm->wdt, s)); }
     g = GemmArgs();
     g.A = lm->hn; g.lda = D; g.W = w.w1; g.ldw = D; g.bias = w.b1; g.C = lm->hid; g.ldc = F;
     g.M = M; g.N = F; g.K = D; g.act = ACT_RELU; g.c_dtype = lm->wdt;
@@ -317,10 +333,12 @@ static int run_heads(ssrb_lm* lm, const int* gather_idx, int M, void* hl, void* 
 }
 
 static int enqueue_step(ssrb_lm* lm, cudaStream_t s) {
-    SSRB_TRY(launch_embed_step(lm->d_next_tok, lm->d_state, lm->R, lm->rpu, lm->K, lm->D, lm->audio_emb, lm->V, lm->pe,
-                               lm->alpha_a, lm->x, s));
+    { ProfScope ps(lm, PC_SMALL, s);
+      SSRB_TRY(launch_embed_step(lm->d_next_tok, lm->d_state, lm->R, lm->rpu, lm->K, lm->D, lm->audio_emb, lm->V, lm->pe,
+                                 lm->alpha_a, lm->x, s)); }
     for (int n = 0; n < lm->L; n++) SSRB_TRY(run_layer(lm, n, lm->R, false, 0, 0, s));
     SSRB_TRY(run_heads(lm, nullptr, lm->R, lm->hlast, lm->hh, lm->logits, s));
+    ProfScope ps(lm, PC_SAMPLE, s);
     SSRB_TRY(launch_sample(lm->logits, lm->d_state, lm->d_seq_len, lm->d_next_tok, lm->d_gen_tok, lm->noise, lm->d_iter,
                            lm->sp, s));
     return 0;
@@ -448,7 +466,10 @@ int ssrb_lm_decode(ssrb_lm* lm, int n_steps, void* stream) {
         SSRB_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
         cudaGraph_t gr = nullptr;
         SSRB_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+        const unsigned long long before = g_launch_count;
         const int rc = enqueue_step(lm, cs);
+        lm->graph_kernels = g_launch_count - before;
+        g_launch_count = before;                 // captured, not launched
         cudaError_t ce = cudaStreamEndCapture(cs, &gr);
         cudaStreamDestroy(cs);
         if (rc) { if (gr) cudaGraphDestroy(gr); return rc; }
@@ -457,6 +478,7 @@ int ssrb_lm_decode(ssrb_lm* lm, int n_steps, void* stream) {
         cudaGraphDestroy(gr);
     }
     for (int i = 0; i < n_steps; i++) SSRB_CUDA(cudaGraphLaunch(lm->graph, s));
+    g_launch_count += lm->graph_kernels * (unsigned long long)n_steps;
     return 0;
 }
 
@@ -547,6 +569,37 @@ int ssrb_lm_step_bytes(ssrb_lm* lm, void* stream, double* weight_bytes, double* 
     for (int r = 0; r < lm->R; r++)
         if (!st[r / lm->rpu].done) kv += L * 2.0 * D * e * ((double)seq[r] + 1.0 /*read S+1*/ + 1.0 /*write 1*/);
     if (kv_bytes) *kv_bytes = kv;
+    return 0;
+}
+
+int ssrb_lm_profile_steps(ssrb_lm* lm, int n_steps, void* stream, double* ms_by_class, double* total_ms) {
+    SSRB_CHECK(lm && lm->R > 0 && n_steps > 0, "no active batch");
+    SSRB_CUDA(cudaSetDevice(lm->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaEvent_t t0, t1;
+    SSRB_CUDA(cudaEventCreate(&t0)); SSRB_CUDA(cudaEventCreate(&t1));
+    lm->prof = true; lm->prof_ev.clear();
+    SSRB_CUDA(cudaEventRecord(t0, s));
+    int rc = 0;
+    for (int i = 0; i < n_steps && !rc; i++) rc = enqueue_step(lm, s);
+    cudaEventRecord(t1, s);
+    lm->prof = false;
+    cudaError_t ce = cudaStreamSynchronize(s);
+    double acc[PC_COUNT] = {0, 0, 0, 0};
+    for (auto& t : lm->prof_ev) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, std::get<1>(t), std::get<2>(t));
+        acc[std::get<0>(t)] += ms;
+        cudaEventDestroy(std::get<1>(t)); cudaEventDestroy(std::get<2>(t));
+    }
+    lm->prof_ev.clear();
+    float tot = 0.f;
+    cudaEventElapsedTime(&tot, t0, t1);
+    cudaEventDestroy(t0); cudaEventDestroy(t1);
+    if (rc) return rc;
+    SSRB_CUDA(ce);
+    if (ms_by_class) for (int i = 0; i < PC_COUNT; i++) ms_by_class[i] = acc[i] / n_steps;
+    if (total_ms) *total_ms = tot / n_steps;
     return 0;
 }
 

@@ -181,14 +181,13 @@ class SSR_Speech:
         return out[0]
 
     @torch.no_grad()
-    def inference_batch(self, xs: List[torch.Tensor], ys: List[torch.Tensor], mask_intervals: List, prompt_xs=None,
-                        prompts=None, top_k: int = -100, top_p: float = 1.0, temperature: float = 1.0,
-                        stop_repetition: int = -1, silence_tokens: Sequence[int] = (1388, 1898, 131),
-                        cfg_coef: float = 1.5, cfg_stride: int = 1, aug_text: bool = False, aug_context: bool = False,
-                        cfg_pretrained: bool = False, uncond_xs=None, noise: Optional[torch.Tensor] = None,
-                        seed: Optional[int] = None, device=None, poll_every: int = 16):
-        """xs[i]: [Lx_i] int64 phoneme ids; ys[i]: [T_i, K] int64 codes; mask_intervals[i]: [M_i, 2].
-        Returns a list of (res [1,K,T_new] int64 (device), marks [1,T_new] int64 (CPU), masks, non_mask_intervals)."""
+    def open_batch(self, xs: List[torch.Tensor], ys: List[torch.Tensor], mask_intervals: List, prompt_xs=None,
+                   prompts=None, top_k: int = -100, top_p: float = 1.0, temperature: float = 1.0,
+                   stop_repetition: int = -1, silence_tokens: Sequence[int] = (1388, 1898, 131),
+                   cfg_coef: float = 1.5, cfg_stride: int = 1, aug_text: bool = False, aug_context: bool = False,
+                   cfg_pretrained: bool = False, uncond_xs=None, noise: Optional[torch.Tensor] = None,
+                   seed: Optional[int] = None, device=None):
+        """Prologue of the loop: host sequence surgery, prefill of every row and the first sample (asynchronous)."""
         if cfg_pretrained:
             raise NotImplementedError("cfg_pretrained=True (key-padding on the uncond row, ssr.py:631-638) is not used "
                                       "by any reference entry point and is not implemented")
@@ -265,24 +264,38 @@ class SSR_Speech:
             full = torch.ones(self._cap[3], U, K, cfg.n_audio_tokens, dtype=torch.float32)
             full[:min(nz.shape[0], self._cap[3])] = nz[:self._cap[3]]
             noise_dev = full.to(self._device).contiguous()
+        self._keep = (text, prom, tl, pl, ns, noise_dev)      # host arrays must outlive the async begin
         with torch.cuda.device(self._device):
             st = _lib.stream_ptr()
-            ev0, ev1, ev2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
             _lib.check(lib.ssrb_lm_begin(self._h, C.byref(batch), C.byref(sp),
                                          C.c_void_p(noise_dev.data_ptr()) if noise_dev is not None else None, st), "ssrb_lm_begin")
             ev1.record()
+        return {"U": U, "preps": preps, "dev": dev, "ev0": ev0, "ev1": ev1}
+
+    @torch.no_grad()
+    def inference_batch(self, xs, ys, mask_intervals, poll_every: int = 16, **kw):
+        """xs[i]: [Lx_i] int64 phoneme ids; ys[i]: [T_i, K] int64 codes; mask_intervals[i]: [M_i, 2]; the remaining
+        keyword arguments are those of `inference` (plus uncond_xs / noise / seed / device).
+        Returns a list of (res [1,K,T_new] int64 (device), marks [1,T_new] int64 (CPU), masks, non_mask_intervals)."""
+        ob = self.open_batch(xs, ys, mask_intervals, **kw)
+        lib = _lib.load()
+        U, preps, dev = ob["U"], ob["preps"], ob["dev"]
+        cfg, K = self.cfg, self.cfg.n_codebooks
+        with torch.cuda.device(self._device):
+            st = _lib.stream_ptr()
+            ev2 = torch.cuda.Event(enable_timing=True)
             nd, it = C.c_int(0), C.c_int(0)
-            done = 0
             while True:
                 _lib.check(lib.ssrb_lm_poll(self._h, st, C.byref(nd), C.byref(it)), "ssrb_lm_poll")
-                done = nd.value
-                if done >= U or it.value >= self._cap[3] + 1:
+                if nd.value >= U or it.value >= self._cap[3] + 1:
                     break
                 _lib.check(lib.ssrb_lm_decode(self._h, int(poll_every), st), "ssrb_lm_decode")
             ev2.record()
             torch.cuda.synchronize()
-            self.last_stats = {"prefill_ms": ev0.elapsed_time(ev1), "decode_ms": ev1.elapsed_time(ev2), "iterations": it.value}
+            self.last_stats = {"prefill_ms": ob["ev0"].elapsed_time(ob["ev1"]), "decode_ms": ob["ev1"].elapsed_time(ev2),
+                               "iterations": it.value}
             results = []
             buf = np.zeros((self._cap[3], K), dtype=np.int32)
             span_len = (C.c_int32 * _lib.MAX_SPANS)()
