@@ -3,7 +3,7 @@
 // Owns the packed weights, the in-place KV cache [layer][K|V][row][head][slot][128], the fp32 residual
 // stream and the per-utterance decode state.  One decode iteration of the reference's `while True`
 // loop (models/ssr.py:671-771) is enqueued as
-//     embed -> 16 x (LN1, QKV GEMM, KV append, attention, out-proj GEMM(+res), LN2, FFN1 GEMM(ReLU),
+//     embed -> 16 x (LN1, QKV GEMM, attention (+ in-place KV append), out-proj GEMM(+res), LN2, FFN1 GEMM(ReLU),
 //     FFN2 GEMM(+res)) -> final LN -> head GEMM(GELU) -> head GEMM -> sample/state kernel
 // and replayed as a CUDA graph, with no host synchronisation inside the loop.
 #include <map>
@@ -295,8 +295,7 @@ static int run_layer(ssrb_lm* lm, int n, int M, bool prefill, int n_rows, int ma
         SSRB_TRY(launch_attn_prefill(lm->qkv, D, H, kc, vc, lm->wdt, lm->cfg.max_seq, n_rows, lm->d_row_ids,
                                      lm->d_row_start, lm->d_row_len, max_len, lm->ao, lm->wdt, s));
     } else {
-        { ProfScope ps(lm, PC_SMALL, s); SSRB_TRY(launch_kv_append(lm->qkv, M, D, H, nullptr, nullptr, lm->d_seq_len, kc, vc, lm->wdt, lm->cfg.max_seq, s)); }
-        ProfScope ps(lm, PC_ATTN, s);
+        ProfScope ps(lm, PC_ATTN, s);   // the decode attention kernel also appends this step's K/V row in place
         SSRB_TRY(launch_attn_decode(lm->qkv, M, D, H, kc, vc, lm->wdt, lm->cfg.max_seq, lm->d_seq_len, lm->d_state,
                                     lm->rpu, lm->attn_ws, lm->tickets, lm->ao, lm->wdt, s));
     }

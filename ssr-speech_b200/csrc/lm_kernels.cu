@@ -179,7 +179,7 @@ size_t attn_decode_ws_floats(int R, int H, int Smax) { return (size_t)R * H * at
 
 template <typename T, typename TO>
 __global__ void __launch_bounds__(128) attn_decode_kernel(const float* __restrict__ qkv, int D, int H,
-                                                          const T* __restrict__ kc, const T* __restrict__ vc, int Smax,
+                                                          const T* kc, const T* vc, int Smax,
                                                           const int* __restrict__ seq_len, const UttState* __restrict__ st,
                                                           int rpu, float* __restrict__ ws, int* __restrict__ tickets,
                                                           TO* __restrict__ out) {
@@ -195,11 +195,23 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const float* __restric
     load8(qkv + (int64_t)r * 3 * D + h * 128 + dl, q);
 #pragma unroll
     for (int i = 0; i < 8; i++) q[i] *= scale;
+    // fused in-place KV append: the CTA whose key range ends at the new position stores this step's K/V row
+    // (the reference re-materialises the whole cache instead: activation.py:626-631, ssr.py:685-686)
+    if (s1 == n_keys) {
+        if (warp == 0) {
+            float nv[8];
+            load8(qkv + (int64_t)r * 3 * D + (1 + half) * D + h * 128 + dl, nv);
+            T* dst = const_cast<T*>(half ? vc : kc) + (((int64_t)r * H + h) * Smax + (n_keys - 1)) * 128 + dl;
+            store8(dst, nv);
+        }
+        __syncthreads();
+    }
     const T* kb = kc + ((int64_t)r * H + h) * Smax * 128 + dl;
     const T* vb = vc + ((int64_t)r * H + h) * Smax * 128 + dl;
     float mrun = -INFINITY, lrun = 0.f, o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     constexpr int U = 4;
-    for (int kp0 = s0 + warp * 2 + half; kp0 < s1; kp0 += 8 * U) {
+    for (int kq = s0 + warp * 2; kq < s1; kq += 8 * U) {   // warp-uniform trip count (full-mask shuffles inside)
+        const int kp0 = kq + half;
         float kk[U][8], sc[U];
 #pragma unroll
         for (int j = 0; j < U; j++) {
@@ -220,23 +232,25 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const float* __restric
             sc[j] = kp < s1 ? p : -INFINITY;
             mnew = fmaxf(mnew, sc[j]);
         }
-        const float corr = __expf(mrun - mnew);   // mrun = -inf on the first pass -> 0
-        lrun *= corr;
+        if (mnew > -INFINITY) {                      // this half-warp has seen at least one key
+            const float corr = __expf(mrun - mnew);   // mrun = -inf on the first pass -> 0
+            lrun *= corr;
 #pragma unroll
-        for (int i = 0; i < 8; i++) o[i] *= corr;
+            for (int i = 0; i < 8; i++) o[i] *= corr;
 #pragma unroll
-        for (int j = 0; j < U; j++) {
-            const int kp = kp0 + j * 8;
-            if (kp < s1) {
-                float vv[8];
-                load8(vb + (int64_t)kp * 128, vv);
-                const float p = __expf(sc[j] - mnew);
-                lrun += p;
+            for (int j = 0; j < U; j++) {
+                const int kp = kp0 + j * 8;
+                if (kp < s1) {
+                    float vv[8];
+                    load8(vb + (int64_t)kp * 128, vv);
+                    const float p = __expf(sc[j] - mnew);
+                    lrun += p;
 #pragma unroll
-                for (int i = 0; i < 8; i++) o[i] = fmaf(p, vv[i], o[i]);
+                    for (int i = 0; i < 8; i++) o[i] = fmaf(p, vv[i], o[i]);
+                }
             }
+            mrun = mnew;
         }
-        mrun = mnew;
     }
     // merge the 8 (warp, half) partial states of this CTA
     __shared__ float sm_m[8], sm_l[8], sm_o[8][128];

@@ -65,6 +65,7 @@ class SSR_Speech:
         self._cap = None         # (max_rows, max_seq, max_prefill_tokens, max_steps)
         self.training = False
         self.last_stats: Dict[str, float] = {}
+        self.poll_every = 16     # decode iterations enqueued between two `done` polls
 
     # ---- nn.Module-like surface used by inference_v2.py:198-204 -------------------------------------
     def load_state_dict(self, state_dict, strict: bool = True):
@@ -275,11 +276,12 @@ class SSR_Speech:
         return {"U": U, "preps": preps, "dev": dev, "ev0": ev0, "ev1": ev1}
 
     @torch.no_grad()
-    def inference_batch(self, xs, ys, mask_intervals, poll_every: int = 16, **kw):
+    def inference_batch(self, xs, ys, mask_intervals, poll_every: Optional[int] = None, **kw):
         """xs[i]: [Lx_i] int64 phoneme ids; ys[i]: [T_i, K] int64 codes; mask_intervals[i]: [M_i, 2]; the remaining
         keyword arguments are those of `inference` (plus uncond_xs / noise / seed / device).
         Returns a list of (res [1,K,T_new] int64 (device), marks [1,T_new] int64 (CPU), masks, non_mask_intervals)."""
         ob = self.open_batch(xs, ys, mask_intervals, **kw)
+        poll_every = int(poll_every or self.poll_every)
         lib = _lib.load()
         U, preps, dev = ob["U"], ob["preps"], ob["dev"]
         cfg, K = self.cfg, self.cfg.n_codebooks
