@@ -126,7 +126,7 @@ def test_bf16_greedy_runs_and_is_deterministic(model_bf16, gold_dir):
     a = run_case(model_bf16, g)[0].cpu()
     b = run_case(model_bf16, g)[0].cpu()
     assert torch.equal(a, b)
-    assert a.shape[1] == 4 and a.min() >= 0 and a.max() < cfg_tiny().audio_vocab_size
+    assert a.shape[1] == 4 and a.min() >= 0 and a.max() < cfg_tiny().n_audio_tokens
 
 
 def test_philox_sampling_is_seed_deterministic(model_fp32, gold_dir):
