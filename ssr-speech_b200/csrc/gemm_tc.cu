@@ -10,17 +10,17 @@
 // Two shapes of the same pipeline:
 //   SWAP  (decode, M <= 128 rows): the WEIGHT tile is the 128-row MMA "A" operand, the activations are the
 //         MMA "B" operand (N = rows padded to 16/32/64/128).  The step is HBM-bound on the weight stream, so
-//         the grid is (N/128 tiles) x split-K slices sized to put >= 2 CTAs on every SM; fp32 partials go to
-//         an L2-resident workspace and the last-arriving CTA of a tile reduces them in a fixed order
-//         (deterministic) and applies the epilogue.
+//         the grid is (N/128 tiles) x split-K slices; the slices of one tile form a THREAD-BLOCK CLUSTER
+//         (<= 8 CTAs).  Each CTA parks its fp32 partial tile in its own shared memory, the cluster barriers,
+//         and every CTA reduces an interleaved subset of rows by reading its peers' tiles through
+//         distributed shared memory (ld.shared::cluster) in a fixed order (deterministic), then applies
+//         bias / activation / residual and stores — no global workspace, no atomics.
 //   FLAT  (prefill, large M): activations are the 128-row operand, a 128-wide weight tile is the N operand.
 //
 // warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue.
 #include <cuda.h>
 
-#include <map>
 #include <mutex>
-#include <tuple>
 
 #include "common.cuh"
 #include "../../include/ssr_b200.h"
@@ -33,6 +33,7 @@ constexpr int BK = 64;                 // bf16 elements per k-block = one 128-by
 constexpr int P_ROWS = 128;            // MMA M
 constexpr int P_BYTES = P_ROWS * BK * 2;
 constexpr int MAX_GROUPS = 4;
+constexpr int MAX_SPLITS = 8;          // portable cluster size
 
 struct TmaPair { CUtensorMap p, q; };
 struct TmaGroup { TmaPair g[MAX_GROUPS]; };
@@ -43,7 +44,6 @@ struct TcParams {
     const float* residual; long long ldr;
     void* C; long long ldc, c_gs; int c_dtype;
     int act;
-    float* ws; int* tickets; int Mpad;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -87,6 +87,20 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
     for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ float ld_dsmem(uint32_t local_addr, uint32_t rank) {
+    uint32_t ra; float v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_addr), "r"(rank));
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+    return v;
+}
 
 __device__ __forceinline__ float apply_act(float v, int act) {
     if (act == ACT_RELU) return fmaxf(v, 0.f);
@@ -99,7 +113,10 @@ template <int QROWS> struct TcCfg {
     static constexpr int STAGE_BYTES = P_BYTES + Q_BYTES;
     static constexpr int STAGES = QROWS >= 128 ? 3 : 4;
     static constexpr int TMEM_COLS = QROWS < 32 ? 32 : QROWS;
-    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
+    static constexpr int PART_BYTES = QROWS * 128 * 4;                    // fp32 partial tile parked for the cluster reduce
+    static_assert(PART_BYTES <= RING_BYTES, "partial tile must fit in the drained TMA ring");
+    static constexpr size_t SMEM = (size_t)RING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 template <int QROWS, bool SWAP>
@@ -107,22 +124,19 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ Tm
     using Cfg = TcCfg<QROWS>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B tiles need 1024 B alignment
-    const uint32_t bar_base = base + Cfg::STAGES * Cfg::STAGE_BYTES;
+    const uint32_t bar_base = base + Cfg::RING_BYTES;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
     const uint32_t accum_bar = bar_base + 8u * (2 * Cfg::STAGES);
     const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 1);
-    __shared__ int s_last;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int grp = blockIdx.z;
-    // tile coordinates
-    int p_row0, q_row0, kb0, kb1, split = 0;
+    int p_row0, q_row0, kb0, kb1;
     if (SWAP) {
         p_row0 = blockIdx.x * P_ROWS;            // output feature n0
         q_row0 = 0;                              // activation rows 0..QROWS
-        split = blockIdx.y;
-        kb0 = split * prm.kb_per_split;
+        kb0 = blockIdx.y * prm.kb_per_split;     // split-K slice (= rank in the cluster)
         kb1 = min(prm.nkb, kb0 + prm.kb_per_split);
     } else {
         q_row0 = blockIdx.x * QROWS;             // n0
@@ -147,6 +161,11 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ Tm
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    const bool clustered = SWAP && prm.splits > 1;
+    const int lg = warp & 3;                             // TMEM lane group an epilogue warp may access
+    const int nl = lg * 32 + lane;                       // row of the 128-row operand owned by an epilogue thread
+    const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16);
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -182,66 +201,52 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ Tm
             umma_commit(accum_bar);
         }
     } else {
-        // ===== epilogue: TMEM -> registers -> global =====
-        const int lg = warp & 3;                         // TMEM lane group this warp may access
-        const int prow = p_row0 + lg * 32 + lane;        // row of the 128-row operand this thread owns
-        const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16);
-        const int et = threadIdx.x - 64;                 // 0..127
+        // ===== epilogue: TMEM -> registers -> (smem partial | global) =====
         if (nk > 0) {
             mbar_wait(accum_bar, 0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
         if (SWAP) {
-            const int n = prow;
+            const int n = p_row0 + nl;
             const bool nok = n < prm.N;
-            const float bv = (prm.bias && nok) ? prm.bias[grp * prm.bias_gs + n] : 0.f;
-            auto finish = [&](int r, float v) {
-                v = apply_act(v + bv, prm.act);
-                if (prm.residual) v += prm.residual[(long long)r * prm.ldr + n];
-                const long long o = grp * prm.c_gs + (long long)r * prm.ldc + n;
-                if (prm.c_dtype == SSRB_DTYPE_F32) reinterpret_cast<float*>(prm.C)[o] = v;
-                else reinterpret_cast<bf16*>(prm.C)[o] = __float2bfloat16_rn(v);
-            };
-            float* wsg = prm.ws + (size_t)grp * prm.splits * prm.Mpad * prm.N;
+            if (!clustered) {
+                const float bv = (prm.bias && nok) ? prm.bias[grp * prm.bias_gs + n] : 0.f;
 #pragma unroll 1
-            for (int c0 = 0; c0 < QROWS; c0 += 16) {
-                if (c0 >= prm.M) break;
-                float v[16];
-                if (nk > 0) tmem_ld16(taddr + c0, v);
-                else {
+                for (int c0 = 0; c0 < QROWS; c0 += 16) {
+                    if (c0 >= prm.M) break;
+                    float v[16];
+                    tmem_ld16(taddr + c0, v);
 #pragma unroll
-                    for (int j = 0; j < 16; j++) v[j] = 0.f;
-                }
-#pragma unroll
-                for (int j = 0; j < 16; j++) {
-                    const int r = c0 + j;
-                    if (r < prm.M && nok) {
-                        if (prm.splits == 1) finish(r, v[j]);
-                        else wsg[((size_t)split * prm.Mpad + r) * prm.N + n] = v[j];
+                    for (int j = 0; j < 16; j++) {
+                        const int r = c0 + j;
+                        if (r < prm.M && nok) {
+                            float x = apply_act(v[j] + bv, prm.act);
+                            if (prm.residual) x += prm.residual[(long long)r * prm.ldr + n];
+                            const long long o = grp * prm.c_gs + (long long)r * prm.ldc + n;
+                            if (prm.c_dtype == SSRB_DTYPE_F32) reinterpret_cast<float*>(prm.C)[o] = x;
+                            else reinterpret_cast<bf16*>(prm.C)[o] = __float2bfloat16_rn(x);
+                        }
                     }
                 }
-            }
-            if (prm.splits > 1) {
-                __threadfence();
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                const int tile = grp * gridDim.x + blockIdx.x;
-                if (et == 0) {
-                    const int t = atomicAdd(&prm.tickets[tile], 1);
-                    s_last = (t == prm.splits - 1);
-                    if (s_last) prm.tickets[tile] = 0;
-                }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (s_last && nok) {
-                    __threadfence();
-                    for (int r = 0; r < prm.M; r++) {
-                        float acc = 0.f;
-                        for (int s = 0; s < prm.splits; s++) acc += __ldcg(wsg + ((size_t)s * prm.Mpad + r) * prm.N + n);
-                        finish(r, acc);
+            } else {
+                // park the fp32 partial tile [r][128 n] in this CTA's smem (the TMA ring is fully drained: every MMA
+                // that read it has completed before accum_bar fired)
+#pragma unroll 1
+                for (int c0 = 0; c0 < QROWS; c0 += 16) {
+                    if (c0 >= prm.M) break;
+                    float v[16];
+                    if (nk > 0) tmem_ld16(taddr + c0, v);
+                    else {
+#pragma unroll
+                        for (int j = 0; j < 16; j++) v[j] = 0.f;
                     }
+#pragma unroll
+                    for (int j = 0; j < 16; j++)
+                        asm volatile("st.shared.f32 [%0], %1;" ::"r"(base + (uint32_t)(((c0 + j) * 128 + nl) * 4)), "f"(v[j]) : "memory");
                 }
             }
         } else {
-            const int m = prow;
+            const int m = p_row0 + nl;
             const bool mok = m < prm.M;
 #pragma unroll 1
             for (int c0 = 0; c0 < QROWS; c0 += 16) {
@@ -281,7 +286,33 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ Tm
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
-    __syncthreads();
+
+    __syncwarp();                                             // reconverge the single-lane producer / MMA warps
+    if (clustered) {
+        // ===== split-K reduction across the cluster through distributed shared memory =====
+        cluster_sync_all();                                 // every CTA's partial tile is parked and visible
+        if (warp >= 2) {
+            const uint32_t rank = cluster_ctarank();
+            const int n = p_row0 + nl;
+            if (n < prm.N) {
+                const float bv = prm.bias ? prm.bias[grp * prm.bias_gs + n] : 0.f;
+                for (int r = (int)rank; r < prm.M; r += prm.splits) {     // interleaved rows: balanced for any M
+                    const uint32_t la = base + (uint32_t)((r * 128 + nl) * 4);
+                    float acc = 0.f;
+#pragma unroll 8
+                    for (int s = 0; s < prm.splits; s++) acc += ld_dsmem(la, (uint32_t)s);    // fixed order
+                    float x = apply_act(acc + bv, prm.act);
+                    if (prm.residual) x += prm.residual[(long long)r * prm.ldr + n];
+                    const long long o = grp * prm.c_gs + (long long)r * prm.ldc + n;
+                    if (prm.c_dtype == SSRB_DTYPE_F32) reinterpret_cast<float*>(prm.C)[o] = x;
+                    else reinterpret_cast<bf16*>(prm.C)[o] = __float2bfloat16_rn(x);
+                }
+            }
+        }
+        cluster_sync_all();                                   // peers may still be reading this CTA's smem
+    } else {
+        __syncthreads();
+    }
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
@@ -323,9 +354,11 @@ int make_map(CUtensorMap* m, const void* ptr, long long rows, long long cols, lo
 
 int qrows_for(int M) { return M <= 16 ? 16 : (M <= 32 ? 32 : (M <= 64 ? 64 : 128)); }
 
+// split-K factor: a power of two <= 8 (cluster size) that divides the k-blocks, >= 4 k-blocks per CTA, enough CTAs to cover
+// the 148 SMs once (each CTA keeps 4 x 24 KB of TMA loads in flight, which is what saturates HBM — not the CTA count)
 int pick_splits(int tiles, int nkb) {
     int s = 1;
-    while (s * 2 <= nkb / 4 && tiles * s < 296) s *= 2;     // >= 4 k-blocks per CTA, aim for >= 2 CTAs per SM
+    while (s * 2 <= MAX_SPLITS && nkb % (s * 2) == 0 && nkb / (s * 2) >= 4 && tiles * s < 148) s *= 2;
     return s;
 }
 
@@ -337,7 +370,14 @@ int launch_tc(const TmaGroup& maps, const TcParams& prm, dim3 grid, cudaStream_t
         SSRB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<QROWS, SWAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
         attr_done = true;
     }
-    SSRB_LAUNCH((gemm_tc_kernel<QROWS, SWAP>), grid, 192, Cfg::SMEM, s, maps, prm);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = Cfg::SMEM; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = (SWAP ? prm.splits : 1); attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    SSRB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<QROWS, SWAP>, maps, prm));
+    g_launch_count++;
     return 0;
 }
 
@@ -353,13 +393,9 @@ bool gemm_tc_supported(const GemmArgs& g) {
     return g.M > 0 && g.N > 0;
 }
 
-size_t gemm_tc_workspace_bytes(int max_rows_decode, int max_n) {
-    // split-K partials: splits(<=32) x Mpad x N x groups(folded into N budget) + tickets
-    const size_t mpad = (size_t)(max_rows_decode <= 128 ? qrows_for(max_rows_decode) : 128);
-    return (size_t)32 * mpad * (size_t)max_n * 4 + 65536;
-}
+size_t gemm_tc_workspace_bytes(int, int) { return 0; }    // the split-K reduction lives in distributed shared memory
 
-int gemm_tc(const GemmArgs& g, void* workspace, size_t workspace_bytes, cudaStream_t s) {
+int gemm_tc(const GemmArgs& g, void*, size_t, cudaStream_t s) {
     SSRB_CHECK(gemm_tc_supported(g), "gemm_tc: unsupported problem");
     TmaGroup maps;
     memset(&maps, 0, sizeof(maps));
@@ -373,15 +409,7 @@ int gemm_tc(const GemmArgs& g, void* workspace, size_t workspace_bytes, cudaStre
         const int q = qrows_for(g.M);
         const int tiles = cdiv(g.N, P_ROWS);
         prm.splits = pick_splits(tiles * g.groups, prm.nkb);
-        prm.kb_per_split = cdiv(prm.nkb, prm.splits);
-        prm.Mpad = q;
-        const size_t ws_need = (size_t)g.groups * prm.splits * q * g.N * 4;
-        const size_t tick_off = (workspace_bytes >= 65536) ? workspace_bytes - 65536 : 0;
-        if (prm.splits > 1) {
-            SSRB_CHECK(workspace && ws_need <= tick_off && (size_t)tiles * g.groups * 4 <= 65536, "gemm_tc: split-K workspace too small");
-            prm.ws = reinterpret_cast<float*>(workspace);
-            prm.tickets = reinterpret_cast<int*>(reinterpret_cast<char*>(workspace) + tick_off);
-        }
+        prm.kb_per_split = prm.nkb / prm.splits;
         for (int i = 0; i < g.groups; i++) {
             SSRB_TRY(make_map(&maps.g[i].p, W + i * g.w_gs, g.N, g.K, g.ldw, P_ROWS));
             SSRB_TRY(make_map(&maps.g[i].q, A + i * g.a_gs, g.M, g.K, g.lda, q));
@@ -394,7 +422,7 @@ int gemm_tc(const GemmArgs& g, void* workspace, size_t workspace_bytes, cudaStre
             default: return launch_tc<128, true>(maps, prm, grid, s);
         }
     }
-    prm.splits = 1; prm.kb_per_split = prm.nkb; prm.Mpad = 0;
+    prm.splits = 1; prm.kb_per_split = prm.nkb;
     SSRB_TRY(make_map(&maps.g[0].p, A, g.M, g.K, g.lda, P_ROWS));
     SSRB_TRY(make_map(&maps.g[0].q, W, g.N, g.K, g.ldw, 128));
     dim3 grid(cdiv(g.N, 128), cdiv(g.M, P_ROWS), 1);

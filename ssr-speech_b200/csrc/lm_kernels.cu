@@ -175,7 +175,7 @@ int launch_kv_append(const float* qkv, int M, int D, int H, const int* rows, con
 // =================================================================================================
 constexpr int ATT_CHUNK = 256;    // keys per split
 int attn_decode_nsplit(int Smax) { return cdiv(Smax, ATT_CHUNK); }
-size_t attn_decode_ws_floats(int R, int H, int Smax) { return (size_t)R * H * attn_decode_nsplit(Smax) * 130; }
+size_t attn_decode_ws_floats(int R, int H, int Smax) { return (size_t)R * H * (size_t)attn_decode_tma_nsplit(Smax) * 130; }   // the finer of the two splits
 
 template <typename T, typename TO>
 __global__ void __launch_bounds__(128) attn_decode_kernel(const float* __restrict__ qkv, int D, int H,
@@ -308,6 +308,10 @@ int launch_attn_decode(const float* qkv, int R, int D, int H, const void* kcache
                     (const float*)vcache, Smax, seq_len, st, rpu, ws, tickets, (float*)out);
     } else {
         SSRB_CHECK(out_dtype == SSRB_DTYPE_BF16, "attn_decode: bf16 cache implies bf16 activations");
+        static const bool simple = [] { const char* e = getenv("SSRB_ATTN_SIMPLE"); return e && e[0] == '1'; }();
+        if (!simple)
+            return launch_attn_decode_tma(qkv, R, D, H, const_cast<void*>(kcache), const_cast<void*>(vcache), Smax, seq_len, st,
+                                          rpu, ws, tickets, out, s);
         SSRB_LAUNCH((attn_decode_kernel<bf16, bf16>), grid, 128, 0, s, qkv, D, H, (const bf16*)kcache,
                     (const bf16*)vcache, Smax, seq_len, st, rpu, ws, tickets, (bf16*)out);
     }
