@@ -48,6 +48,41 @@ extern unsigned long long g_launch_count;   // kernels launched by this library 
         SSRB_CUDA(cudaGetLastError());                                                            \
     } while (0)
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------
+// Kernels of the decode chain are launched with cudaLaunchAttributeProgrammaticStreamSerialization: a kernel may start
+// while its predecessor is still running, so EVERY kernel calls pdl_wait() before touching anything a predecessor
+// writes (only immutable weights may be prefetched earlier) and pdl_launch_dependents() as early as possible.
+// Both are no-ops when the kernel was launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();     // SSRB_NO_PDL=1 disables the launch attribute (lm_engine.cu)
+
+template <typename... KArgs, typename... Args>
+int launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, int cluster_y, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (cluster_y > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 1; attr[na].val.clusterDim.y = (unsigned)cluster_y; attr[na].val.clusterDim.z = 1;
+        na++;
+    }
+    if (pdl_enabled()) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        na++;
+    }
+    cfg.attrs = attr; cfg.numAttrs = na;
+    SSRB_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+    g_launch_count++;
+    return 0;
+}
+
+// launch of a kernel that belongs to a PDL chain (the kernel itself calls pdl_launch_dependents()/pdl_wait())
+#define SSRB_LAUNCH_PDL(kernel, grid, block, smem, stream, ...)                                   \
+    SSRB_TRY(::ssrb::launch_pdl(kernel, dim3(grid), dim3(block), (smem), (stream), 1, __VA_ARGS__))
+
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -22,6 +22,8 @@ __device__ __forceinline__ void epilogue_store(const GemmArgs& g, int grp, int m
 // ---- skinny path: M <= MR rows, one warp per output column, 128-bit weight loads -----------------------
 template <typename T, typename TC, int MR>
 __global__ void __launch_bounds__(256) gemv_rows_kernel(GemmArgs g) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int grp = blockIdx.z;
     const int n = blockIdx.x * 8 + warp;
@@ -54,6 +56,8 @@ __global__ void __launch_bounds__(256) gemv_rows_kernel(GemmArgs g) {
 // ---- tiled path: 64x64x16 tiles, 256 threads, 4x4 outputs per thread -----------------------------------
 template <typename T, typename TC>
 __global__ void __launch_bounds__(256) gemm_tile_kernel(GemmArgs g) {
+    pdl_launch_dependents();
+    pdl_wait();
     constexpr int BM = 64, BN = 64, BK = 16, PAD = 4;
     __shared__ __align__(16) float As[2][BK][BM + PAD];
     __shared__ __align__(16) float Ws[2][BK][BN + PAD];
@@ -109,13 +113,13 @@ static int launch_simt(const GemmArgs& g, cudaStream_t s) {
     SSRB_CHECK(g.lda % 8 == 0 && g.ldw % 8 == 0, "gemm_simt: leading dims must be multiples of 8 elements");
     if (g.M <= 4 && g.K % 256 == 0) {
         dim3 grid(cdiv(g.N, 8), 1, g.groups);
-        if (g.M <= 1) SSRB_LAUNCH((gemv_rows_kernel<T, TC, 1>), grid, 256, 0, s, g);
-        else if (g.M <= 2) SSRB_LAUNCH((gemv_rows_kernel<T, TC, 2>), grid, 256, 0, s, g);
-        else SSRB_LAUNCH((gemv_rows_kernel<T, TC, 4>), grid, 256, 0, s, g);
+        if (g.M <= 1) SSRB_LAUNCH_PDL((gemv_rows_kernel<T, TC, 1>), grid, 256, 0, s, g);
+        else if (g.M <= 2) SSRB_LAUNCH_PDL((gemv_rows_kernel<T, TC, 2>), grid, 256, 0, s, g);
+        else SSRB_LAUNCH_PDL((gemv_rows_kernel<T, TC, 4>), grid, 256, 0, s, g);
         return 0;
     }
     dim3 grid(cdiv(g.N, 64), cdiv(g.M, 64), g.groups);
-    SSRB_LAUNCH((gemm_tile_kernel<T, TC>), grid, 256, 0, s, g);
+    SSRB_LAUNCH_PDL((gemm_tile_kernel<T, TC>), grid, 256, 0, s, g);
     return 0;
 }
 

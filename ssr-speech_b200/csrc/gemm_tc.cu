@@ -130,6 +130,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ Tm
     const uint32_t accum_bar = bar_base + 8u * (2 * Cfg::STAGES);
     const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 1);
 
+    pdl_launch_dependents();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int grp = blockIdx.z;
     int p_row0, q_row0, kb0, kb1;
@@ -170,7 +171,22 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ Tm
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            for (int i = 0; i < nk; i++) {
+            // PDL: the WEIGHT operand is immutable, so its first STAGES tiles are requested before griddepcontrol.wait —
+            // the weight stream of this GEMM starts while the previous kernel of the chain is still draining.
+            const int npre = min(nk, Cfg::STAGES);
+            for (int i = 0; i < npre; i++) {
+                mbar_expect_tx(full_bar(i), Cfg::STAGE_BYTES);
+                const uint32_t sp = base + i * Cfg::STAGE_BYTES;
+                if (SWAP) tma_load_2d(sp, mapP, full_bar(i), (kb0 + i) * BK, p_row0);
+                else tma_load_2d(sp + P_BYTES, mapQ, full_bar(i), (kb0 + i) * BK, q_row0);
+            }
+            pdl_wait();                                   // activations come from the preceding kernel
+            for (int i = 0; i < npre; i++) {
+                const uint32_t sp = base + i * Cfg::STAGE_BYTES;
+                if (SWAP) tma_load_2d(sp + P_BYTES, mapQ, full_bar(i), (kb0 + i) * BK, q_row0);
+                else tma_load_2d(sp, mapP, full_bar(i), (kb0 + i) * BK, p_row0);
+            }
+            for (int i = npre; i < nk; i++) {
                 const int s = i % Cfg::STAGES;
                 const uint32_t ph = (i / Cfg::STAGES) & 1;
                 mbar_wait(empty_bar(s), ph ^ 1);
@@ -202,6 +218,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ Tm
         }
     } else {
         // ===== epilogue: TMEM -> registers -> (smem partial | global) =====
+        pdl_wait();                                       // residual / output buffers belong to the kernel chain
         if (nk > 0) {
             mbar_wait(accum_bar, 0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -370,15 +387,7 @@ int launch_tc(const TmaGroup& maps, const TcParams& prm, dim3 grid, cudaStream_t
         SSRB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<QROWS, SWAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
         attr_done = true;
     }
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = grid; cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = Cfg::SMEM; cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = (SWAP ? prm.splits : 1); attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    SSRB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<QROWS, SWAP>, maps, prm));
-    g_launch_count++;
-    return 0;
+    return launch_pdl(gemm_tc_kernel<QROWS, SWAP>, grid, dim3(192), Cfg::SMEM, s, SWAP ? prm.splits : 1, maps, prm);
 }
 
 }  // namespace

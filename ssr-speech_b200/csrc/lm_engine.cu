@@ -18,6 +18,10 @@ namespace ssrb {
 static thread_local std::string g_err;
 void set_error(const std::string& m) { g_err = m; }
 unsigned long long g_launch_count = 0;
+bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("SSRB_NO_PDL"); return !(e && e[0] == '1'); }();
+    return on;
+}
 
 template <typename T>
 __global__ void convert_kernel(const float* __restrict__ src, T* __restrict__ dst, int64_t n) {

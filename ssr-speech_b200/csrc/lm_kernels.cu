@@ -15,6 +15,8 @@ __global__ void __launch_bounds__(256) embed_prefill_kernel(const PosDesc* __res
                                                             const float* __restrict__ audio_emb, int V,
                                                             const float* __restrict__ pe, float alpha_t, float alpha_a,
                                                             float* __restrict__ x) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int m = blockIdx.x;
     const PosDesc pd = desc[m];
     const float* per = pe + (int64_t)pd.pe_idx * D;
@@ -38,6 +40,8 @@ __global__ void __launch_bounds__(256) embed_prefill_kernel(const PosDesc* __res
 __global__ void __launch_bounds__(256) embed_step_kernel(const int* __restrict__ next_tok, const UttState* __restrict__ st,
                                                          int rpu, int K, int D, const float* __restrict__ audio_emb, int V,
                                                          const float* __restrict__ pe, float alpha_a, float* __restrict__ x) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int r = blockIdx.x, u = r / rpu;
     const int* tk = next_tok + u * K;
     const int pos = st[u].y_len;
@@ -57,13 +61,13 @@ __global__ void __launch_bounds__(256) embed_step_kernel(const int* __restrict__
 int launch_embed_prefill(const PosDesc* desc, int M, int D, const float* text_emb, const float* audio_emb, int V,
                          const float* pe, float alpha_t, float alpha_a, float* x, cudaStream_t s) {
     if (M <= 0) return 0;
-    SSRB_LAUNCH(embed_prefill_kernel, M, 256, 0, s, desc, D, text_emb, audio_emb, V, pe, alpha_t, alpha_a, x);
+    SSRB_LAUNCH_PDL(embed_prefill_kernel, M, 256, 0, s, desc, D, text_emb, audio_emb, V, pe, alpha_t, alpha_a, x);
     return 0;
 }
 int launch_embed_step(const int* next_tok, const UttState* st, int R, int rpu, int K, int D, const float* audio_emb,
                       int V, const float* pe, float alpha_a, float* x, cudaStream_t s) {
     SSRB_CHECK(K == 4, "embed_step: K must be 4");
-    SSRB_LAUNCH(embed_step_kernel, R, 256, 0, s, next_tok, st, rpu, K, D, audio_emb, V, pe, alpha_a, x);
+    SSRB_LAUNCH_PDL(embed_step_kernel, R, 256, 0, s, next_tok, st, rpu, K, D, audio_emb, V, pe, alpha_a, x);
     return 0;
 }
 
@@ -75,6 +79,8 @@ template <typename TO>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const int* __restrict__ idx, int D,
                                                         const float* __restrict__ w, const float* __restrict__ b,
                                                         TO* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float red[8];
     __shared__ float stat[2];
     const int m = blockIdx.x;
@@ -127,8 +133,8 @@ int launch_layernorm(const float* x, const int* idx, int M, int D, const float* 
                      int out_dtype, cudaStream_t s) {
     if (M <= 0) return 0;
     SSRB_CHECK(D <= 2048, "layernorm: d_model > 2048 not supported");
-    if (out_dtype == SSRB_DTYPE_F32) SSRB_LAUNCH(layernorm_kernel<float>, M, 256, 0, s, x, idx, D, w, b, (float*)out);
-    else SSRB_LAUNCH(layernorm_kernel<bf16>, M, 256, 0, s, x, idx, D, w, b, (bf16*)out);
+    if (out_dtype == SSRB_DTYPE_F32) SSRB_LAUNCH_PDL(layernorm_kernel<float>, M, 256, 0, s, x, idx, D, w, b, (float*)out);
+    else SSRB_LAUNCH_PDL(layernorm_kernel<bf16>, M, 256, 0, s, x, idx, D, w, b, (bf16*)out);
     return 0;
 }
 
@@ -142,6 +148,8 @@ __global__ void __launch_bounds__(256) kv_append_kernel(const float* __restrict_
                                                         const int* __restrict__ rows, const int* __restrict__ slots,
                                                         const int* __restrict__ seq_len, T* __restrict__ kc,
                                                         T* __restrict__ vc, int Smax) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int m = blockIdx.x;
     const int r = rows ? rows[m] : m;
     const int slot = slots ? slots[m] : seq_len[m];
@@ -161,9 +169,9 @@ int launch_kv_append(const float* qkv, int M, int D, int H, const int* rows, con
                      void* kcache, void* vcache, int cache_dtype, int Smax, cudaStream_t s) {
     if (M <= 0) return 0;
     if (cache_dtype == SSRB_DTYPE_F32)
-        SSRB_LAUNCH(kv_append_kernel<float>, M, 256, 0, s, qkv, D, H, rows, slots, seq_len, (float*)kcache, (float*)vcache, Smax);
+        SSRB_LAUNCH_PDL(kv_append_kernel<float>, M, 256, 0, s, qkv, D, H, rows, slots, seq_len, (float*)kcache, (float*)vcache, Smax);
     else
-        SSRB_LAUNCH(kv_append_kernel<bf16>, M, 256, 0, s, qkv, D, H, rows, slots, seq_len, (bf16*)kcache, (bf16*)vcache, Smax);
+        SSRB_LAUNCH_PDL(kv_append_kernel<bf16>, M, 256, 0, s, qkv, D, H, rows, slots, seq_len, (bf16*)kcache, (bf16*)vcache, Smax);
     return 0;
 }
 
@@ -175,7 +183,7 @@ int launch_kv_append(const float* qkv, int M, int D, int H, const int* rows, con
 // =================================================================================================
 constexpr int ATT_CHUNK = 256;    // keys per split
 int attn_decode_nsplit(int Smax) { return cdiv(Smax, ATT_CHUNK); }
-size_t attn_decode_ws_floats(int R, int H, int Smax) { return (size_t)R * H * (size_t)attn_decode_tma_nsplit(Smax) * 130; }   // the finer of the two splits
+size_t attn_decode_ws_floats(int R, int H, int Smax) { return (size_t)R * H * (size_t)attn_decode_tma_max_nsplit(Smax) * 130; }   // the finer of the two splits
 
 template <typename T, typename TO>
 __global__ void __launch_bounds__(128) attn_decode_kernel(const float* __restrict__ qkv, int D, int H,
@@ -183,6 +191,8 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const float* __restric
                                                           const int* __restrict__ seq_len, const UttState* __restrict__ st,
                                                           int rpu, float* __restrict__ ws, int* __restrict__ tickets,
                                                           TO* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int h = blockIdx.x, r = blockIdx.y, z = blockIdx.z, nz = gridDim.z;
     if (st[r / rpu].done) return;
     const int n_keys = seq_len[r] + 1;
@@ -304,7 +314,7 @@ int launch_attn_decode(const float* qkv, int R, int D, int H, const void* kcache
     dim3 grid(H, R, attn_decode_nsplit(Smax));
     if (cache_dtype == SSRB_DTYPE_F32) {
         SSRB_CHECK(out_dtype == SSRB_DTYPE_F32, "attn_decode: fp32 cache implies fp32 activations");
-        SSRB_LAUNCH((attn_decode_kernel<float, float>), grid, 128, 0, s, qkv, D, H, (const float*)kcache,
+        SSRB_LAUNCH_PDL((attn_decode_kernel<float, float>), grid, 128, 0, s, qkv, D, H, (const float*)kcache,
                     (const float*)vcache, Smax, seq_len, st, rpu, ws, tickets, (float*)out);
     } else {
         SSRB_CHECK(out_dtype == SSRB_DTYPE_BF16, "attn_decode: bf16 cache implies bf16 activations");
@@ -312,7 +322,7 @@ int launch_attn_decode(const float* qkv, int R, int D, int H, const void* kcache
         if (!simple)
             return launch_attn_decode_tma(qkv, R, D, H, const_cast<void*>(kcache), const_cast<void*>(vcache), Smax, seq_len, st,
                                           rpu, ws, tickets, out, s);
-        SSRB_LAUNCH((attn_decode_kernel<bf16, bf16>), grid, 128, 0, s, qkv, D, H, (const bf16*)kcache,
+        SSRB_LAUNCH_PDL((attn_decode_kernel<bf16, bf16>), grid, 128, 0, s, qkv, D, H, (const bf16*)kcache,
                     (const bf16*)vcache, Smax, seq_len, st, rpu, ws, tickets, (bf16*)out);
     }
     return 0;
@@ -331,6 +341,8 @@ __global__ void __launch_bounds__(128) attn_prefill_kernel(const float* __restri
                                                            const T* __restrict__ kc, const T* __restrict__ vc, int Smax,
                                                            const int* __restrict__ row_ids, const int* __restrict__ row_start,
                                                            const int* __restrict__ row_len, TO* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ __align__(16) float Ks[PF_K][PF_PITCH];
     __shared__ __align__(16) float Vs[PF_K][PF_PITCH];
     const int qt = blockIdx.x, h = blockIdx.y, ri = blockIdx.z;
@@ -432,10 +444,10 @@ int launch_attn_prefill(const float* qkv, int D, int H, const void* kcache, cons
     if (n_rows <= 0) return 0;
     dim3 grid(cdiv(max_len, PF_Q), H, n_rows);
     if (cache_dtype == SSRB_DTYPE_F32)
-        SSRB_LAUNCH((attn_prefill_kernel<float, float>), grid, 128, 0, s, qkv, D, H, (const float*)kcache,
+        SSRB_LAUNCH_PDL((attn_prefill_kernel<float, float>), grid, 128, 0, s, qkv, D, H, (const float*)kcache,
                     (const float*)vcache, Smax, row_ids, row_start, row_len, (float*)out);
     else
-        SSRB_LAUNCH((attn_prefill_kernel<bf16, bf16>), grid, 128, 0, s, qkv, D, H, (const bf16*)kcache,
+        SSRB_LAUNCH_PDL((attn_prefill_kernel<bf16, bf16>), grid, 128, 0, s, qkv, D, H, (const bf16*)kcache,
                     (const bf16*)vcache, Smax, row_ids, row_start, row_len, (bf16*)out);
     (void)out_dtype;
     return 0;
@@ -502,6 +514,8 @@ __global__ void __launch_bounds__(256) sample_kernel(const float* __restrict__ l
                                                      int* __restrict__ seq_len, int* __restrict__ next_tok,
                                                      int* __restrict__ gen_tok, const float* __restrict__ noise,
                                                      int* __restrict__ iter_counter, SampleParams p) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ GroupRed red;
     __shared__ int s_samples[4];
     __shared__ int s_argmax0;
@@ -674,7 +688,7 @@ int launch_sample(const float* logits, UttState* st, int* seq_len, int* next_tok
                   int* iter_counter, const SampleParams& p, cudaStream_t s) {
     SSRB_CHECK(p.K == 4, "sample: n_codebooks must be 4");
     SSRB_CHECK(p.V <= 64 * SMP_NPT, "sample: audio vocabulary too large for the sampling kernel");
-    SSRB_LAUNCH(sample_kernel, p.n_utt, 256, 0, s, logits, st, seq_len, next_tok, gen_tok, noise, iter_counter, p);
+    SSRB_LAUNCH_PDL(sample_kernel, p.n_utt, 256, 0, s, logits, st, seq_len, next_tok, gen_tok, noise, iter_counter, p);
     return 0;
 }
 
