@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--prompt-sec", type=float, default=10.0)
     ap.add_argument("--lx", type=int, default=101, help="phonemes per utterance (generation length = 10*lx - prompt frames - 9)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--codec-precision", default="bf16", choices=["bf16", "fp32"], help="decoder/wmdecode convolutions: bf16 tcgen05 or fp32 CUDA cores (encode is always fp32)")
     ap.add_argument("--no-watermark", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-iters", type=int, default=12)
@@ -270,7 +271,7 @@ def workload_config(args):
     return {"workload": f"BASELINE configs[2]: English TTS 830M random-init, cfg_coef=1.5 cfg_stride=5 aug_text, top_p=0.8, "
                         f"{args.prompt_sec:g} s prompt -> {(10 * args.lx - T - 9) / 50:g} s generation, batch {args.batch}/GPU",
             "batch_per_gpu": args.batch, "prompt_frames": T, "text_len": args.lx, "rows_per_gpu": 2 * args.batch,
-            "precision": args.precision, "watermark_decode": not args.no_watermark,
+            "precision": args.precision, "codec_decoder_precision": args.codec_precision, "watermark_decode": not args.no_watermark,
             "l2_policy": "inputs larger than L2: each decode iteration streams 1.65 GB of weights + the KV cache",
             "parallelism": f"dp{args.gpus} (utterances sharded, weights replicated)"}
 
@@ -307,7 +308,7 @@ def main():
     model.load_state_dict(make_lm_state_dict(cfg, seed=0, pin_eog_bias=True))
     model.to(dev).eval()
     ccfg = CodecConfig()
-    codec = WMEncodecModel(ccfg, max_batch_chunk=8)
+    codec = WMEncodecModel(ccfg, max_batch_chunk=16, precision=args.codec_precision)
     codec.load_state_dict(make_codec_state_dict(ccfg, seed=0))
     codec.to(dev)
     cal = 0.1 * torch.randn(4, 1, 32000, generator=torch.Generator().manual_seed(7))

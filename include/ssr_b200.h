@@ -148,6 +148,9 @@ typedef struct {
     int kernel_size, residual_kernel_size, last_kernel_size, compress, lstm_layers;
     int n_q, bins;
     int max_batch_chunk;                  /* utterances processed per internal pass (bounds workspace) */
+    int tensor_cores;                     /* 0: fp32 CUDA-core kernels everywhere (parity mode; encode is always fp32 because the
+                                             RVQ indices must be reproducible); 1: decode / wmdecode run their SEANet
+                                             convolutions as bf16 tcgen05 GEMMs over channels-last activations           */
 } ssrb_codec_config;
 
 int ssrb_codec_create(const ssrb_codec_config* cfg, int device, ssrb_codec** out);

@@ -37,7 +37,7 @@ class CodecConfigC(C.Structure):
     _fields_ = [("channels", C.c_int), ("dimension", C.c_int), ("n_filters", C.c_int), ("n_ratios", C.c_int),
                 ("ratios", C.c_int * 8), ("kernel_size", C.c_int), ("residual_kernel_size", C.c_int),
                 ("last_kernel_size", C.c_int), ("compress", C.c_int), ("lstm_layers", C.c_int), ("n_q", C.c_int),
-                ("bins", C.c_int), ("max_batch_chunk", C.c_int)]
+                ("bins", C.c_int), ("max_batch_chunk", C.c_int), ("tensor_cores", C.c_int)]
 
 
 EXPORTS = [

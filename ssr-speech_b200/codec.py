@@ -20,7 +20,11 @@ from .config import CodecConfig
 
 
 class WMEncodecModel:
-    def __init__(self, cfg: CodecConfig = CodecConfig(), max_batch_chunk: int = 8):
+    def __init__(self, cfg: CodecConfig = CodecConfig(), max_batch_chunk: int = 8, precision: str = "fp32"):
+        """precision: "fp32" = fp32 CUDA-core kernels everywhere (parity mode); "bf16" = decode / wmdecode on the
+        tcgen05 tensor cores (bf16 operands, fp32 accumulate).  encode() is always fp32: its RVQ indices must be reproducible."""
+        assert precision in ("fp32", "bf16"), precision
+        self.precision = precision
         self.cfg = cfg
         self.sample_rate = cfg.sample_rate
         self.channels = cfg.channels
@@ -78,7 +82,8 @@ class WMEncodecModel:
         conf = _lib.CodecConfigC(channels=c.channels, dimension=c.dimension, n_filters=c.n_filters, n_ratios=len(c.ratios),
                                  ratios=ratios, kernel_size=c.kernel_size, residual_kernel_size=c.residual_kernel_size,
                                  last_kernel_size=c.last_kernel_size, compress=c.compress, lstm_layers=c.lstm, n_q=c.n_q,
-                                 bins=c.bins, max_batch_chunk=self.max_batch_chunk)
+                                 bins=c.bins, max_batch_chunk=self.max_batch_chunk,
+                                 tensor_cores=1 if self.precision == "bf16" else 0)
         lib = _lib.load()
         h = C.c_void_p()
         with torch.cuda.device(self._device):

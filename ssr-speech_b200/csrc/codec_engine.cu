@@ -11,13 +11,20 @@
 #include <vector>
 
 #include "codec_kernels.cuh"
+#include "conv_tc.cuh"
 #include "../../include/ssr_b200.h"
 
 using namespace ssrb;
 
 namespace {
 
-struct ConvW { float* w = nullptr; float* b = nullptr; int d0 = 0, d1 = 0, k = 0; bool has_w = false, has_b = false; };
+struct ConvW {
+    float* w = nullptr; float* b = nullptr; int d0 = 0, d1 = 0, k = 0; bool has_w = false, has_b = false;
+    std::vector<float> hw, hb;          // host copies (folded weight, bias) for the tensor-core repack
+};
+// tensor-core operand of one convolution: W' [taps][N][Cw] bf16 (conv_tc.cu), fp32 bias (+ per-mark bias for wm_proj)
+struct TcW { bf16* w = nullptr; float* bias = nullptr; float* bias_alt = nullptr; int taps = 0, N = 0, Cw = 0, bias_mod = 0; };
+struct ClT { bf16* raw = nullptr; bf16* act = nullptr; int C = 0, T = 0; };   // channels-last tensor [B][G+T+G][C]
 struct LstmW {
     float *wih[4] = {}, *whh[4] = {}, *bsum[4] = {};
     std::vector<float> bih[4], bhh[4];
@@ -46,6 +53,9 @@ struct ssrb_codec {
     float* wm_embed = nullptr; bool has_wm_embed = false;
     unsigned int* bar = nullptr;
     Arena arena;
+    std::map<std::string, TcW> tcw;
+    std::vector<float> wm_embed_host;   // renormalised rows
+    bool use_tc = false;
 };
 
 static int dalloc(void** p, size_t bytes) { SSRB_CUDA(cudaMalloc(p, bytes ? bytes : 16)); return 0; }
@@ -59,6 +69,7 @@ int ssrb_codec_create(const ssrb_codec_config* c, int device, ssrb_codec** out) 
     SSRB_CUDA(cudaSetDevice(device));
     ssrb_codec* cd = new ssrb_codec();
     cd->cfg = *c; cd->device = device;
+    cd->use_tc = c->tensor_cores != 0;
     if (cd->cfg.max_batch_chunk <= 0 || cd->cfg.max_batch_chunk > 32) cd->cfg.max_batch_chunk = 8;
     cd->hop = 1;
     for (int i = 0; i < c->n_ratios; i++) cd->hop *= c->ratios[i];
@@ -76,6 +87,7 @@ void ssrb_codec_destroy(ssrb_codec* c) {
     cudaDeviceSynchronize();
     for (auto& kv : c->convs) { cudaFree(kv.second.w); cudaFree(kv.second.b); }
     for (auto& kv : c->lstms) for (int l = 0; l < 4; l++) { cudaFree(kv.second.wih[l]); cudaFree(kv.second.whh[l]); cudaFree(kv.second.bsum[l]); }
+    for (auto& kv : c->tcw) { cudaFree(kv.second.w); cudaFree(kv.second.bias); cudaFree(kv.second.bias_alt); }
     cudaFree(c->codebooks); cudaFree(c->cb_sq); cudaFree(c->wm_embed); cudaFree(c->bar); cudaFree(c->arena.base);
     delete c;
 }
@@ -126,6 +138,7 @@ int ssrb_codec_load_tensor(ssrb_codec* c, const char* name_c, const float* host,
             if (nr > 1.0f) { const float sc = 1.0f / (nr + 1e-7f); for (int d = 0; d < E; d++) w[r * E + d] *= sc; }
         }
         SSRB_CUDA(cudaMemcpy(c->wm_embed, w.data(), n * 4, cudaMemcpyHostToDevice));
+        c->wm_embed_host = w;
         c->has_wm_embed = true;
         return 0;
     }
@@ -154,11 +167,11 @@ int ssrb_codec_load_tensor(ssrb_codec* c, const char* name_c, const float* host,
     const std::string prefix = name.substr(0, dot + 1), leaf = name.substr(dot + 1);
     if (prefix.find("conv.conv.") == std::string::npos && prefix.find("convtr.convtr.") == std::string::npos) return 0;
     ConvW& W = c->convs[prefix];
-    if (leaf == "bias") { SSRB_TRY(upload_new(&W.b, host, n)); W.has_b = true; return 0; }
+    if (leaf == "bias") { SSRB_TRY(upload_new(&W.b, host, n)); W.hb.assign(host, host + n); W.has_b = true; return 0; }
     if (leaf == "weight") {
         SSRB_CHECK(ndim == 3, "conv weight must be 3-D");
         W.d0 = (int)shape[0]; W.d1 = (int)shape[1]; W.k = (int)shape[2];
-        SSRB_TRY(upload_new(&W.w, host, n)); W.has_w = true; return 0;
+        SSRB_TRY(upload_new(&W.w, host, n)); W.hw.assign(host, host + n); W.has_w = true; return 0;
     }
     if (leaf == "weight_g" || leaf == "weight_v") {
         Pending& P = c->pending[prefix];
@@ -176,7 +189,7 @@ int ssrb_codec_load_tensor(ssrb_codec* c, const char* name_c, const float* host,
                 for (int64_t j = 0; j < inner; j++) w[i * inner + j] = P.v[i * inner + j] * sc;
             }
             W.d0 = (int)P.vshape[0]; W.d1 = (int)P.vshape[1]; W.k = (int)P.vshape[2];
-            SSRB_TRY(upload_new(&W.w, w.data(), w.size())); W.has_w = true;
+            SSRB_TRY(upload_new(&W.w, w.data(), w.size())); W.hw = w; W.has_w = true;
             c->pending.erase(prefix);
         }
         return 0;
@@ -300,6 +313,199 @@ static int decoder(Ctx& x, const std::string& p, Tensor in, Tensor* out) {
     return 0;
 }
 
+
+// =====================================================================================================================
+// Tensor-core path (cfg.tensor_cores): decode / wmdecode convolutions as bf16 tap-GEMMs over channels-last activations
+// (conv_tc.cu).  The frame-rate region (first decoder conv, LSTMs, wm_proj0, last encoder conv) stays on the fp32 kernels.
+// =====================================================================================================================
+static inline int pad64(int c) { return (c + 63) / 64 * 64; }
+static inline unsigned short f2bf(float f) {          // round-to-nearest-even fp32 -> bf16 (host)
+    unsigned int u; memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (unsigned short)((u >> 16) | 0x40);
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (unsigned short)(u >> 16);
+}
+static inline float eluf(float x) { return x > 0.f ? x : std::expm1(x); }
+
+enum TcKind { TC_CONV = 0, TC_CONVS = 1, TC_CONVTR = 2, TC_WMPROJ = 3 };
+
+// builds (once) the repacked operand of convolution `key`
+static int get_tcw(ssrb_codec* c, const std::string& key, int kind, int stride, const TcW** out) {
+    auto it = c->tcw.find(key);
+    if (it != c->tcw.end()) { *out = &it->second; return 0; }
+    const ConvW* W;
+    SSRB_TRY(get_conv(c, key, &W));
+    SSRB_CHECK(!W->hw.empty() && !W->hb.empty(), ("host weights missing for " + key).c_str());
+    TcW t;
+    std::vector<unsigned short> wp;
+    std::vector<float> bias, bias_alt;
+    const int k = W->k;
+    if (kind == TC_CONV || kind == TC_WMPROJ) {             // W [Cout][Cin][k], stride 1
+        const int Cout = W->d0, Cin_all = W->d1;
+        const int E = kind == TC_WMPROJ ? c->cfg.dimension / 16 : 0;
+        const int Cin = Cin_all - E;
+        t.taps = k; t.N = pad64(Cout); t.Cw = pad64(Cin); t.bias_mod = t.N;
+        wp.assign((size_t)t.taps * t.N * t.Cw, 0);
+        for (int q = 0; q < k; q++)
+            for (int n = 0; n < Cout; n++)
+                for (int ci = 0; ci < Cin; ci++)
+                    wp[((size_t)q * t.N + n) * t.Cw + ci] = f2bf(W->hw[((size_t)n * Cin_all + ci) * k + q]);
+        bias.assign(t.N, 0.f);
+        for (int n = 0; n < Cout; n++) bias[n] = W->hb[n];
+        if (kind == TC_WMPROJ) {                            // cat([skip, emb]) -> ELU -> 1x1 conv: fold the embedding rows into 2 biases
+            SSRB_CHECK((int)c->wm_embed_host.size() == 2 * E && k == 1, "wm_proj repack: bad wm_embed");
+            bias_alt = bias;
+            for (int n = 0; n < Cout; n++)
+                for (int m = 0; m < 2; m++) {
+                    float acc = 0.f;
+                    for (int e = 0; e < E; e++) acc += W->hw[(size_t)n * Cin_all + Cin + e] * eluf(c->wm_embed_host[m * E + e]);
+                    (m ? bias_alt : bias)[n] += acc;
+                }
+        }
+    } else if (kind == TC_CONVS) {                          // W [Cout][Cin][2s]: view rows of s time steps
+        const int Cout = W->d0, Cin = W->d1, s = stride;
+        SSRB_CHECK(k == 2 * s && Cin % 64 == 0, "strided conv repack: unsupported shape");
+        t.taps = 2; t.N = pad64(Cout); t.Cw = s * Cin; t.bias_mod = t.N;
+        wp.assign((size_t)t.taps * t.N * t.Cw, 0);
+        for (int q = 0; q < 2; q++)
+            for (int n = 0; n < Cout; n++)
+                for (int r = 0; r < s; r++)
+                    for (int ci = 0; ci < Cin; ci++)
+                        wp[((size_t)q * t.N + n) * t.Cw + r * Cin + ci] = f2bf(W->hw[((size_t)n * Cin + ci) * k + q * s + r]);
+        bias.assign(t.N, 0.f);
+        for (int n = 0; n < Cout; n++) bias[n] = W->hb[n];
+    } else {                                                // TC_CONVTR: W [Cin][Cout][2s]; tap 0 = x[i-1] (k = p+s), tap 1 = x[i] (k = p)
+        const int Cin = W->d0, Cout = W->d1, s = stride;
+        SSRB_CHECK(k == 2 * s && Cin % 64 == 0 && Cout % 16 == 0, "convtr repack: unsupported shape");
+        t.taps = 2; t.N = s * Cout; t.Cw = Cin; t.bias_mod = Cout;
+        SSRB_CHECK(t.N % 64 == 0, "convtr repack: s*Cout must be a multiple of 64");
+        wp.assign((size_t)t.taps * t.N * t.Cw, 0);
+        for (int p = 0; p < s; p++)
+            for (int co = 0; co < Cout; co++)
+                for (int ci = 0; ci < Cin; ci++) {
+                    wp[((size_t)0 * t.N + p * Cout + co) * t.Cw + ci] = f2bf(W->hw[((size_t)ci * Cout + co) * k + p + s]);
+                    wp[((size_t)1 * t.N + p * Cout + co) * t.Cw + ci] = f2bf(W->hw[((size_t)ci * Cout + co) * k + p]);
+                }
+        bias.assign(W->hb.begin(), W->hb.begin() + Cout);
+    }
+    SSRB_TRY(dalloc((void**)&t.w, wp.size() * 2));
+    SSRB_CUDA(cudaMemcpy(t.w, wp.data(), wp.size() * 2, cudaMemcpyHostToDevice));
+    SSRB_TRY(upload_new(&t.bias, bias.data(), bias.size()));
+    if (!bias_alt.empty()) SSRB_TRY(upload_new(&t.bias_alt, bias_alt.data(), bias_alt.size()));
+    c->tcw[key] = t;
+    *out = &c->tcw[key];
+    return 0;
+}
+
+static ClT cl_alloc(Ctx& x, int C, int T, bool raw, bool act) {
+    ClT t; t.C = C; t.T = T;
+    const size_t n = (size_t)x.B * (T + 2 * CL_GUARD) * C;           // bf16 elements = n*2 bytes = n/2 floats
+    if (raw) t.raw = (bf16*)x.c->arena.f((n + 1) / 2);
+    if (act) t.act = (bf16*)x.c->arena.f((n + 1) / 2);
+    if (!x.c->arena.dry) {                                            // guards (and everything else) start as zeros
+        if (raw) cudaMemsetAsync(t.raw, 0, n * 2, x.s);
+        if (act) cudaMemsetAsync(t.act, 0, n * 2, x.s);
+    }
+    return t;
+}
+
+// generic tensor-core convolution on a channels-last input (its ELU'd copy is the operand)
+static int tc_conv(Ctx& x, const std::string& key, int kind, int stride, const ClT& in, const bf16* in_buf, const bf16* residual,
+                   bool want_raw, bool want_act, const long long* marks, int marks_T, int marks_rep, ClT* out) {
+    const TcW* W;
+    SSRB_TRY(get_tcw(x.c, key, kind, stride, &W));
+    const int G = CL_GUARD, C = in.C, T = in.T;
+    ConvTcArgs a;
+    a.x = in_buf; a.B = x.B; a.x_bstride = (long long)(T + 2 * G) * C; a.w = W->w; a.taps = W->taps; a.N = W->N; a.Cw = W->Cw;
+    a.bias = W->bias; a.bias_alt = W->bias_alt; a.bias_mod = W->bias_mod; a.marks = marks; a.marks_T = marks_T; a.marks_rep = marks_rep;
+    int Tout, Cout;
+    if (kind == TC_CONV || kind == TC_WMPROJ) {
+        SSRB_CHECK(W->Cw == C, ("tc conv input width mismatch at " + key).c_str());
+        const int k = W->taps, total = k - 1, padL = total - total / 2;
+        Tout = T; Cout = W->N;
+        a.x_base_off = (long long)(G - padL) * C; a.rows_v = T + G + padL; a.T_rows = T;
+        a.out_off = (long long)G * Cout; a.valid_lo = 0; a.valid_hi = (long long)T * Cout;
+    } else if (kind == TC_CONVS) {
+        SSRB_CHECK(W->Cw == stride * C && T % stride == 0, ("tc strided conv shape mismatch at " + key).c_str());
+        const int padL = stride - stride / 2;
+        Tout = T / stride; Cout = W->N;
+        a.x_base_off = (long long)(G - padL) * C;
+        a.rows_v = (int)((a.x_bstride - a.x_base_off) / W->Cw); a.T_rows = Tout;
+        a.out_off = (long long)G * Cout; a.valid_lo = 0; a.valid_hi = (long long)Tout * Cout;
+    } else {
+        SSRB_CHECK(W->Cw == C, ("tc convtr input width mismatch at " + key).c_str());
+        const int padL = stride - stride / 2;
+        Tout = T * stride; Cout = W->bias_mod;
+        a.x_base_off = (long long)(G - 1) * C; a.rows_v = T + G + 1; a.T_rows = T + 1;
+        a.out_off = (long long)(G - padL) * Cout; a.valid_lo = (long long)padL * Cout; a.valid_hi = a.valid_lo + (long long)Tout * Cout;
+    }
+    *out = cl_alloc(x, Cout, Tout, want_raw, want_act);
+    a.out_raw = out->raw; a.out_act = out->act; a.out_bstride = (long long)(Tout + 2 * G) * Cout;
+    if (residual) { a.res = residual; a.res_bstride = a.out_bstride; a.res_off = (long long)G * Cout; }
+    if (x.c->arena.dry) return 0;
+    return conv_tc(a, x.s);
+}
+// SEANetResnetBlock on the tensor cores: y = x + conv_k1(ELU(conv_k3(ELU(x)))); only ELU(y) (and optionally y) is kept
+static int tc_resblock(Ctx& x, const std::string& prefix, const ClT& in, bool want_raw, ClT* out) {
+    ClT h;
+    SSRB_TRY(tc_conv(x, prefix + "block.1.conv.conv.", TC_CONV, 1, in, in.act, nullptr, false, true, nullptr, 0, 1, &h));
+    return tc_conv(x, prefix + "block.3.conv.conv.", TC_CONV, 1, h, h.act, in.raw, want_raw, true, nullptr, 0, 1, out);
+}
+
+// decoder from the first transposed conv to the waveform; `frame` = ELU'able LSTM output [B,1024,Tf] fp32 channels-first.
+// skips (wm path): ELU'd channels-last skip tensors for stages 1..3, else null.
+static int decoder_tail_tc(Ctx& x, const std::string& p, Tensor frame, const ClT* skips, const long long* marks, int Tf, float* wav_out) {
+    const int* r = x.c->cfg.ratios;
+    ClT cur = cl_alloc(x, frame.C, frame.T, false, true);
+    if (!x.c->arena.dry) SSRB_TRY(launch_cf32_to_cl(frame.p, x.B, frame.C, frame.T, true, cur.act, x.s));
+    int rep = 1;
+    for (int st = 0; st < 4; st++) {
+        ClT up, y;
+        const int tr_idx = 3 + 3 * st;                                  // model.3, 6, 9, 12
+        SSRB_TRY(tc_conv(x, p + "model." + std::to_string(tr_idx) + ".convtr.convtr.", TC_CONVTR, r[st], cur, cur.act, nullptr, true, true,
+                         nullptr, 0, 1, &up));
+        rep *= r[st];
+        if (skips && st < 3) {                                          // out = wm_proj_{st+1}(ELU(cat(skip, emb))) + x   (seanet.py:581-591)
+            ClT o;
+            SSRB_TRY(tc_conv(x, "wmdecoder.wm_proj" + std::to_string(st + 1) + ".1.conv.conv.", TC_WMPROJ, 1, skips[st], skips[st].act, up.raw,
+                             true, true, marks, Tf, rep, &o));
+            up = o;
+        }
+        SSRB_TRY(tc_resblock(x, p + "model." + std::to_string(tr_idx + 1) + ".", up, false, &y));
+        cur = y;
+    }
+    const ConvW* Wl;
+    SSRB_TRY(get_conv(x.c, p + "model.15.conv.conv.", &Wl));
+    if (x.c->arena.dry) return 0;
+    return launch_cl_last_conv(cur.act, x.B, cur.T, cur.C, Wl->w, Wl->b, Wl->k, wav_out, x.s);
+}
+
+// skip encoder of WMSEANetDecoder on the tensor cores: returns ELU'd skips for stages 1..3 (512@T/40, 256@T/8, 128@T/2) and the
+// frame-rate skip3 (fp32 channels-first) for wm_proj0.
+static int skip_encoder_tc(Ctx& x, const std::string& p, const float* wav, int T, ClT* skips /*[3]*/, Tensor* skip3) {
+    const int* r = x.c->cfg.ratios;
+    const int er[4] = {r[3], r[2], r[1], r[0]};
+    const ConvW* W0;
+    SSRB_TRY(get_conv(x.c, p + "model.0.conv.conv.", &W0));
+    ClT z0 = cl_alloc(x, pad64(W0->d0), T, true, true), cur;
+    if (!x.c->arena.dry) SSRB_TRY(launch_cl_first_conv(wav, x.B, T, W0->w, W0->b, W0->d0, W0->k, z0.raw, z0.act, x.s));
+    SSRB_TRY(tc_resblock(x, p + "model.1.", z0, false, &cur));
+    for (int st = 1; st <= 3; st++) {
+        ClT d, y;
+        const int ci = 3 * st;
+        SSRB_TRY(tc_conv(x, p + "model." + std::to_string(ci) + ".conv.conv.", TC_CONVS, er[st - 1], cur, cur.act, nullptr, true, true, nullptr, 0, 1, &d));
+        SSRB_TRY(tc_resblock(x, p + "model." + std::to_string(ci + 1) + ".", d, false, &y));
+        skips[3 - st] = y;                                               // st=1 -> skips[2] (128@T/2) ... st=3 -> skips[0] (512@T/40)
+        cur = y;
+    }
+    ClT d8;
+    SSRB_TRY(tc_conv(x, p + "model.12.conv.conv.", TC_CONVS, er[3], cur, cur.act, nullptr, true, false, nullptr, 0, 1, &d8));
+    Tensor a{x.c->arena.f((size_t)x.B * d8.C * d8.T), d8.C, d8.T}, b;
+    if (!x.c->arena.dry) SSRB_TRY(launch_cl_to_cf32(d8.raw, x.B, d8.C, d8.T, a.p, x.s));
+    if (x.c->cfg.lstm_layers > 0) { SSRB_TRY(lstm(x, p + "model.13.", a, &b)); } else b = a;
+    return conv(x, p + "model.15.conv.conv.", b, 1, true, nullptr, skip3);
+}
+
 // runs `fn` twice: a dry pass to size the arena, then for real
 template <typename F>
 static int run_planned(ssrb_codec* c, F fn) {
@@ -373,6 +579,12 @@ int ssrb_codec_decode(ssrb_codec* c, const int64_t* codes, int B, int Tf, float*
             Tensor z{c->arena.f((size_t)nb * Dm * Tf), Dm, Tf}, out;
             if (!c->arena.dry)
                 SSRB_TRY(launch_rvq_decode((const long long*)codes + (size_t)b0 * nq * Tf, nb, nq, Tf, c->codebooks, c->cfg.bins, Dm, z.p, s));
+            if (c->use_tc) {
+                Tensor a, b;
+                SSRB_TRY(conv(x, "decoder.model.0.conv.conv.", z, 1, false, nullptr, &a));
+                if (c->cfg.lstm_layers > 0) { SSRB_TRY(lstm(x, "decoder.model.1.", a, &b)); } else b = a;
+                return decoder_tail_tc(x, "decoder.", b, nullptr, nullptr, Tf, wav + (size_t)b0 * T);
+            }
             SSRB_TRY(decoder(x, "decoder.", z, &out));
             if (c->arena.dry) return 0;
             SSRB_CHECK(out.C == 1 && out.T == T, "decoder output shape mismatch");
@@ -401,6 +613,17 @@ int ssrb_codec_wmdecode(ssrb_codec* c, const int64_t* codes, const int64_t* mark
             Tensor lat{A.f((size_t)nb * Dm * Tf), Dm, Tf};
             if (!A.dry)
                 SSRB_TRY(launch_rvq_decode((const long long*)codes + (size_t)b0 * nq * Tf, nb, nq, Tf, c->codebooks, c->cfg.bins, Dm, lat.p, s));
+            if (c->use_tc && !mark_logits) {
+                ClT sk[3];
+                Tensor skip3, cat{nullptr, Dm + E, Tf}, o0, a, b;
+                SSRB_TRY(skip_encoder_tc(x, "wmdecoder.skip_encoder.", wav_in + (size_t)b0 * T, T, sk, &skip3));
+                cat.p = A.f((size_t)nb * (Dm + E) * Tf);
+                if (!A.dry) SSRB_TRY(launch_concat_marks(skip3.p, nb, Dm, Tf, mk, Tf, 1, c->wm_embed, E, cat.p, s));
+                SSRB_TRY(conv(x, "wmdecoder.wm_proj0.1.conv.conv.", cat, 1, true, lat.p, &o0));      // + x (seanet.py:577-578)
+                SSRB_TRY(conv(x, "wmdecoder.model.0.conv.conv.", o0, 1, false, nullptr, &a));
+                if (c->cfg.lstm_layers > 0) { SSRB_TRY(lstm(x, "wmdecoder.model.1.", a, &b)); } else b = a;
+                return decoder_tail_tc(x, "wmdecoder.", b, sk, mk, Tf, wav_out + (size_t)b0 * T);
+            }
             // skip encoder over the (partly zeroed) original waveform (seanet.py:559-574)
             Tensor z{const_cast<float*>(wav_in) + (size_t)b0 * T, 1, T}, nx, skips[4];
             SSRB_TRY(encoder_stage(x, "wmdecoder.skip_encoder.", 0, z, &nx)); z = nx;

@@ -323,6 +323,11 @@ __global__ void __launch_bounds__(256) lstm_layer_kernel(const float* __restrict
     // thread -> (unit, batch) for the cell update; c state lives in a register for the whole sequence
     const int cu = tid % LSTM_UPB, cb = tid / LSTM_UPB;
     float c_state = 0.f;
+    float pre_v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (cb < B) {
+        const float* pr = pre + (size_t)cb * 4 * C + u0 + cu;
+        pre_v[0] = pr[0]; pre_v[1] = pr[C]; pre_v[2] = pr[2 * C]; pre_v[3] = pr[3 * C];
+    }
     __syncthreads();
     for (int t = 0; t < T; t++) {
         const float* hprev = hbuf + (size_t)(t & 1) * B * C;
@@ -361,24 +366,29 @@ __global__ void __launch_bounds__(256) lstm_layer_kernel(const float* __restrict
         }
         __syncthreads();
         if (cb < B) {
-            const float* pr = pre + ((size_t)t * B + cb) * 4 * C + u0 + cu;
-            const float gi = g_s[(0 * LSTM_UPB + cu) * 32 + cb] + pr[0];
-            const float gf = g_s[(1 * LSTM_UPB + cu) * 32 + cb] + pr[C];
-            const float gg = g_s[(2 * LSTM_UPB + cu) * 32 + cb] + pr[2 * C];
-            const float go = g_s[(3 * LSTM_UPB + cu) * 32 + cb] + pr[3 * C];
+            const float gi = g_s[(0 * LSTM_UPB + cu) * 32 + cb] + pre_v[0];
+            const float gf = g_s[(1 * LSTM_UPB + cu) * 32 + cb] + pre_v[1];
+            const float gg = g_s[(2 * LSTM_UPB + cu) * 32 + cb] + pre_v[2];
+            const float go = g_s[(3 * LSTM_UPB + cu) * 32 + cb] + pre_v[3];
             c_state = sigmoidf_(gf) * c_state + sigmoidf_(gi) * tanhf(gg);
             const float hv = sigmoidf_(go) * tanhf(c_state);
             hnext[(size_t)cb * C + u0 + cu] = hv;
             hseq[((size_t)t * B + cb) * C + u0 + cu] = hv;
+            if (t + 1 < T) {                                  // input-projection terms of the next step: off the critical path
+                const float* pr = pre + ((size_t)(t + 1) * B + cb) * 4 * C + u0 + cu;
+                pre_v[0] = pr[0]; pre_v[1] = pr[C]; pre_v[2] = pr[2 * C]; pre_v[3] = pr[3 * C];
+            }
         }
-        // grid barrier (monotonic counter; all CTAs are co-resident: cooperative launch)
+        // grid barrier (monotonic counter; all CTAs are co-resident: cooperative launch).  release/acquire at gpu scope
+        // orders the h_t stores of every CTA before the h_t loads of every other CTA.
         __syncthreads();
         if (tid == 0) {
-            __threadfence();
-            atomicAdd(bar, 1u);
             const unsigned int target = G * (unsigned int)(t + 1);
-            while (*((volatile unsigned int*)bar) < target) { }
-            __threadfence();
+            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+            unsigned int v;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+            } while (v < target);
         }
         __syncthreads();
     }

@@ -122,3 +122,61 @@ def test_encode_decode_linearity_of_rvq_decode(small):
     lat = o.rvq_decode(codes)
     back = m.quantize(lat.cuda())                                  # quantising an exact code sum returns stage-0 codes consistent
     assert back.shape == codes.shape
+
+
+# ---- tensor-core (bf16) decoder path: tolerance 1e-2 * max|ref| -----------------------------------
+@pytest.fixture(scope="module")
+def small_tc(gold_dir):
+    g = np.load(os.path.join(gold_dir, "codec_small.npz"))
+    cfg = CodecConfig()
+    sd = make_codec_state_dict(cfg, seed=int(g["weights_seed"]), codebook_mu=g["codebook_mu"], codebook_sigma=g["codebook_sigma"])
+    m = WMEncodecModel(cfg, precision="bf16")
+    m.load_state_dict(sd)
+    return g, cfg, sd, m.to("cuda")
+
+
+def test_tc_decode_waveform(small_tc):
+    g, cfg, sd, m = small_tc
+    wav = m.decode(torch.from_numpy(g["ref_codes"]).cuda())
+    ref = g["ref_dec"]
+    assert tuple(wav.shape) == ref.shape
+    err = np.abs(wav.cpu().numpy() - ref).max()
+    assert err <= 1e-2 * np.abs(ref).max(), (err, np.abs(ref).max())
+    assert np.corrcoef(wav.cpu().numpy().ravel(), ref.ravel())[0, 1] > 0.9995
+
+
+def test_tc_wmdecode_waveform(small_tc):
+    g, cfg, sd, m = small_tc
+    out, _ = m.wmdecode(torch.from_numpy(g["ref_codes"]).cuda(), torch.from_numpy(g["marks"]).cuda(),
+                        torch.from_numpy(g["wav"]).cuda(), return_marks=False)
+    ref = g["ref_wm"]
+    err = np.abs(out.cpu().numpy() - ref).max()
+    assert err <= 1e-2 * np.abs(ref).max(), (err, np.abs(ref).max())
+    assert np.corrcoef(out.cpu().numpy().ravel(), ref.ravel())[0, 1] > 0.9995
+
+
+def test_tc_encode_is_still_fp32_exact(small_tc):
+    """encode() never uses the bf16 path: RVQ indices stay reproducible."""
+    g, cfg, sd, m = small_tc
+    codes, _, emb = m.encode(torch.from_numpy(g["wav"]).cuda())
+    assert np.abs(emb.cpu().numpy() - g["ref_emb"]).max() <= 1e-4 * np.abs(g["ref_emb"]).max()
+    assert (codes.cpu().numpy() == g["ref_codes"]).mean() >= 0.98
+
+
+def test_tc_longer_ragged_batch_matches_fp32_path(small_tc):
+    """3 utterances x 1.3 s (row tiles with ragged tails, several batch items): bf16 tensor-core path vs fp32 path."""
+    g, cfg, sd, m = small_tc
+    ref = WMEncodecModel(cfg, precision="fp32")
+    ref.load_state_dict(sd)
+    ref.to("cuda")
+    gen = torch.Generator().manual_seed(2)
+    Tf = 65
+    codes = torch.randint(0, cfg.bins, (3, 4, Tf), generator=gen).cuda()
+    marks = (torch.rand(3, Tf, generator=gen) > 0.5).long().cuda()
+    wav = (0.1 * torch.randn(3, 1, Tf * 320, generator=gen)).cuda()
+    a = m.decode(codes)
+    b = ref.decode(codes)
+    assert (a - b).abs().max() <= 1e-2 * b.abs().max()
+    a, _ = m.wmdecode(codes, marks, wav, return_marks=False)
+    b, _ = ref.wmdecode(codes, marks, wav, return_marks=False)
+    assert (a - b).abs().max() <= 1e-2 * b.abs().max()
