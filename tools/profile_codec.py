@@ -14,17 +14,19 @@ def main():
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--sec", type=float, default=10.0)
     ap.add_argument("--chunk", type=int, default=8)
+    ap.add_argument("--precision", default="bf16")
     args = ap.parse_args()
     from ssr_speech_b200.codec import WMEncodecModel
     from ssr_speech_b200.config import CodecConfig
     from ssr_speech_b200.synth import make_codec_state_dict
     cfg = CodecConfig()
-    m = WMEncodecModel(cfg, max_batch_chunk=args.chunk)
+    m = WMEncodecModel(cfg, max_batch_chunk=args.chunk, precision=args.precision)
     m.load_state_dict(make_codec_state_dict(cfg, seed=0))
     m.to("cuda:0")
     T = int(args.sec * 50) * 320
     wav = 0.1 * torch.randn(args.batch, 1, T, generator=torch.Generator().manual_seed(0)).cuda()
     codes, _, _ = m.encode(wav)
+    m.wmdecode(codes, torch.zeros(args.batch, T // 320, dtype=torch.long, device='cuda'), wav, return_marks=False)
     marks = torch.zeros(args.batch, T // 320, dtype=torch.long, device="cuda")
     marks[:, T // 640:] = 1
     torch.cuda.synchronize()
