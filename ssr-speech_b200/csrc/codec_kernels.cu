@@ -335,34 +335,49 @@ __global__ void __launch_bounds__(256) lstm_layer_kernel(const float* __restrict
         for (int b0 = 0; b0 < B; b0 += LSTM_BC) {
             const int nb = min(LSTM_BC, B - b0);
             __syncthreads();
-            for (int e = tid; e < LSTM_BC * C; e += 256) {
+            for (int e = tid * 4; e < LSTM_BC * C; e += 1024) {            // C % 4 == 0: a float4 never straddles rows
                 const int bb = e / C;
-                h_s[e] = bb < nb ? __ldcg(hprev + (size_t)(b0 + bb) * C + (e - bb * C)) : 0.f;
+                float4 hv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (bb < nb) hv = __ldcg(reinterpret_cast<const float4*>(hprev + (size_t)(b0 + bb) * C + (e - bb * C)));
+                *reinterpret_cast<float4*>(h_s + e) = hv;
             }
             __syncthreads();
-            float acc[4][LSTM_BC];
+            // 4 gate rows x 8 batch entries per warp; each lane owns 4 consecutive k per 128-wide slab (LDS.128, no bank
+            // conflicts), so one loop trip issues 12 shared loads for 128 independent FMAs
+            float acc[32];
 #pragma unroll
-            for (int i = 0; i < 4; i++)
+            for (int i = 0; i < 32; i++) acc[i] = 0.f;
+            for (int k = lane * 4; k < C; k += 128) {
+                float4 w[4], h[LSTM_BC];
 #pragma unroll
-                for (int j = 0; j < LSTM_BC; j++) acc[i][j] = 0.f;
-            for (int k = lane; k < C; k += 32) {
-                float w[4], h[LSTM_BC];
+                for (int i = 0; i < 4; i++) w[i] = *reinterpret_cast<const float4*>(w_s + (warp * 4 + i) * C + k);
 #pragma unroll
-                for (int i = 0; i < 4; i++) w[i] = w_s[(warp * 4 + i) * C + k];
-#pragma unroll
-                for (int j = 0; j < LSTM_BC; j++) h[j] = h_s[j * C + k];
+                for (int j = 0; j < LSTM_BC; j++) h[j] = *reinterpret_cast<const float4*>(h_s + j * C + k);
 #pragma unroll
                 for (int i = 0; i < 4; i++)
 #pragma unroll
-                    for (int j = 0; j < LSTM_BC; j++) acc[i][j] = fmaf(w[i], h[j], acc[i][j]);
+                    for (int j = 0; j < LSTM_BC; j++) {
+                        float a = acc[i * LSTM_BC + j];
+                        a = fmaf(w[i].x, h[j].x, a); a = fmaf(w[i].y, h[j].y, a);
+                        a = fmaf(w[i].z, h[j].z, a); a = fmaf(w[i].w, h[j].w, a);
+                        acc[i * LSTM_BC + j] = a;
+                    }
             }
+            // halving butterfly: 31 shuffles reduce the 32 accumulators over the 32 lanes; lane L ends with accumulator L
 #pragma unroll
-            for (int i = 0; i < 4; i++)
+            for (int off = 16; off >= 1; off >>= 1) {
+                const bool up = (lane & off) != 0;
 #pragma unroll
-                for (int j = 0; j < LSTM_BC; j++) {
-                    const float v = warp_sum(acc[i][j]);
-                    if (lane == 0 && j < nb) g_s[(warp * 4 + i) * 32 + ((b0 + j) & 31)] = v;
+                for (int i = 0; i < off; i++) {
+                    const float send = up ? acc[i] : acc[i + off];
+                    const float keep = up ? acc[i + off] : acc[i];
+                    acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
                 }
+            }
+            {
+                const int i = lane / LSTM_BC, j = lane % LSTM_BC;
+                if (j < nb) g_s[(warp * 4 + i) * 32 + ((b0 + j) & 31)] = acc[0];
+            }
         }
         __syncthreads();
         if (cb < B) {
