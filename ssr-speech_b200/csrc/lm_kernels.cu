@@ -446,9 +446,12 @@ int launch_attn_prefill(const float* qkv, int D, int H, const void* kcache, cons
     if (cache_dtype == SSRB_DTYPE_F32)
         SSRB_LAUNCH_PDL((attn_prefill_kernel<float, float>), grid, 128, 0, s, qkv, D, H, (const float*)kcache,
                     (const float*)vcache, Smax, row_ids, row_start, row_len, (float*)out);
-    else
+    else {
+        static const bool simt = [] { const char* e = getenv("SSRB_PREFILL_SIMT"); return e && e[0] == '1'; }();
+        if (!simt) return launch_attn_prefill_mma(qkv, D, H, kcache, vcache, Smax, n_rows, row_ids, row_start, row_len, max_len, out, s);
         SSRB_LAUNCH_PDL((attn_prefill_kernel<bf16, bf16>), grid, 128, 0, s, qkv, D, H, (const bf16*)kcache,
                     (const bf16*)vcache, Smax, row_ids, row_start, row_len, (bf16*)out);
+    }
     (void)out_dtype;
     return 0;
 }

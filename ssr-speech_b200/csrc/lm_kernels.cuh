@@ -56,6 +56,9 @@ int attn_decode_nsplit(int Smax);
 int launch_attn_prefill(const float* qkv, int D, int H, const void* kcache, const void* vcache, int cache_dtype,
                         int Smax, int n_rows, const int* row_ids, const int* row_start, const int* row_len,
                         int max_len, void* out, int out_dtype, cudaStream_t s);
+// bf16 tensor-core prefill attention (attn_prefill_mma.cu)
+int launch_attn_prefill_mma(const float* qkv, int D, int H, const void* kcache, const void* vcache, int Smax, int n_rows,
+                            const int* row_ids, const int* row_start, const int* row_len, int max_len, void* out, cudaStream_t s);
 // CFG + logit rules + top-k/top-p + sample + state machine (models/ssr.py:690-754)
 int launch_sample(const float* logits, UttState* st, int* seq_len, int* next_tok, int* gen_tok, const float* noise,
                   int* iter_counter, const SampleParams& p, cudaStream_t s);

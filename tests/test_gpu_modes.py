@@ -65,7 +65,7 @@ def test_scheduling_modes_are_bit_identical(base, env):
     assert other["tf_sha"] == base["tf_sha"]
 
 
-@pytest.mark.parametrize("env", [{"SSRB_GEMM_IMPL": "1"}, {"SSRB_ATTN_SIMPLE": "1"}])
+@pytest.mark.parametrize("env", [{"SSRB_GEMM_IMPL": "1"}, {"SSRB_ATTN_SIMPLE": "1"}, {"SSRB_PREFILL_SIMT": "1"}])
 def test_kernel_variants_agree_within_bf16_tolerance(base, env):
     other = run(env)
     a, b = np.asarray(base["tf_probe"]), np.asarray(other["tf_probe"])
