@@ -175,6 +175,10 @@ int ssrb_codec_decode(ssrb_codec* c, const int64_t* codes_dev, int B, int Tf, fl
 int ssrb_codec_wmdecode(ssrb_codec* c, const int64_t* codes_dev, const int64_t* marks_dev, const float* wav_in_dev,
                         int B, int Tf, float* wav_out_dev, float* mark_logits_dev, void* stream);
 
+/* Debug: arms (dev_buf != NULL) or disarms the in-kernel timeline of the decode-chain kernels.  dev_buf holds cap x 4 u64
+ * records {kernel id, CTA id, globaltimer ns at entry, at exit}; *dev_idx counts records (tools/timeline.py). */
+int ssrb_debug_timeline(unsigned long long* dev_buf, unsigned int* dev_idx, unsigned int cap);
+
 /* ------------------------------------------------------------------------------------------------
  * Stand-alone op hooks used by the unit tests (each runs exactly the kernel the engines use).
  * ---------------------------------------------------------------------------------------------- */

@@ -68,7 +68,9 @@ __global__ void __launch_bounds__(160, 2) attn_decode_tma_kernel(const float* __
     __shared__ float sm_m[8], sm_l[8], sm_o[8][128];
     __shared__ int sm_last;
     pdl_launch_dependents();
+    const int ts = ts_begin(TSK_ATTN);
     pdl_wait();        // everything this kernel reads (state, cache rows of earlier steps, q/k/v) is produced upstream
+    ts_dep(ts);
     const int h = blockIdx.x, r = blockIdx.y, z = blockIdx.z, nz = gridDim.z;
     if (st[r / rpu].done) return;
     const int n_keys = seq_len[r] + 1;
@@ -208,7 +210,7 @@ __global__ void __launch_bounds__(160, 2) attn_decode_tma_kernel(const float* __
         O += sm_o[i][d] * w;
     }
     bf16* op = out + (int64_t)r * D + h * 128 + d;
-    if (nsplit_eff == 1) { *op = __float2bfloat16_rn(O / L); return; }
+    if (nsplit_eff == 1) { *op = __float2bfloat16_rn(O / L); ts_end(ts); return; }
     float* wsp = ws + ((int64_t)(r * H + h) * nz + z) * 130;
     wsp[2 + d] = O;
     if (d == 0) { wsp[0] = M; wsp[1] = L; }
@@ -257,5 +259,7 @@ int launch_attn_decode_tma(const float* qkv, int R, int D, int H, void* kcache, 
     return launch_pdl(attn_decode_tma_kernel, grid, dim3(160), AT_SMEM, s, 1, qkv, D, H, (bf16*)kcache, (bf16*)vcache, Smax, seq_len,
                       st, rpu, ws, tickets, (bf16*)out);
 }
+
+int ts_arm_attn_tma(const TsBuf& t) { return ts_arm_tu(t); }
 
 }  // namespace ssrb

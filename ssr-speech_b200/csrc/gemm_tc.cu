@@ -131,6 +131,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ Tm
     const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 1);
 
     pdl_launch_dependents();
+    const int ts = ts_begin(TSK_GEMM);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int grp = blockIdx.z;
     int p_row0, q_row0, kb0, kb1;
@@ -181,6 +182,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ Tm
                 else tma_load_2d(sp + P_BYTES, mapQ, full_bar(i), (kb0 + i) * BK, q_row0);
             }
             pdl_wait();                                   // activations come from the preceding kernel
+            ts_dep(ts);
             for (int i = 0; i < npre; i++) {
                 const uint32_t sp = base + i * Cfg::STAGE_BYTES;
                 if (SWAP) tma_load_2d(sp + P_BYTES, mapQ, full_bar(i), (kb0 + i) * BK, q_row0);
@@ -195,6 +197,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ Tm
                 tma_load_2d(sp, mapP, full_bar(s), (kb0 + i) * BK, p_row0);
                 tma_load_2d(sp + P_BYTES, mapQ, full_bar(s), (kb0 + i) * BK, q_row0);
             }
+            ts_aux(ts);                                   // all loads issued
         }
     } else if (warp == 1) {
         // ===== MMA issuer (one thread) =====
@@ -330,6 +333,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ Tm
     } else {
         __syncthreads();
     }
+    ts_end(ts);
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
@@ -437,5 +441,7 @@ int gemm_tc(const GemmArgs& g, void*, size_t, cudaStream_t s) {
     dim3 grid(cdiv(g.N, 128), cdiv(g.M, P_ROWS), 1);
     return launch_tc<128, false>(maps, prm, grid, s);
 }
+
+int ts_arm_gemm_tc(const TsBuf& t) { return ts_arm_tu(t); }
 
 }  // namespace ssrb

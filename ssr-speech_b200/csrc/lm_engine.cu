@@ -606,6 +606,12 @@ int ssrb_lm_profile_steps(ssrb_lm* lm, int n_steps, void* stream, double* ms_by_
     return 0;
 }
 
+int ssrb_debug_timeline(unsigned long long* dev_buf, unsigned int* dev_idx, unsigned int cap) {
+    TsBuf t{dev_buf, dev_idx, cap};
+    SSRB_CHECK(!ts_arm_gemm_tc(t) && !ts_arm_attn_tma(t) && !ts_arm_lm_kernels(t), "cudaMemcpyToSymbol failed");
+    return 0;
+}
+
 int ssrb_op_gemm(const void* A, const void* W, const float* bias, const float* residual, float* C, int M, int N, int K,
                  int dtype, int act, int impl, void* stream) {
     GemmArgs g;

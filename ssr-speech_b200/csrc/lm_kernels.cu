@@ -41,7 +41,9 @@ __global__ void __launch_bounds__(256) embed_step_kernel(const int* __restrict__
                                                          int rpu, int K, int D, const float* __restrict__ audio_emb, int V,
                                                          const float* __restrict__ pe, float alpha_a, float* __restrict__ x) {
     pdl_launch_dependents();
+    const int ts = ts_begin(TSK_EMBED);
     pdl_wait();
+    ts_dep(ts);
     const int r = blockIdx.x, u = r / rpu;
     const int* tk = next_tok + u * K;
     const int pos = st[u].y_len;
@@ -80,7 +82,9 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         const float* __restrict__ w, const float* __restrict__ b,
                                                         TO* __restrict__ out) {
     pdl_launch_dependents();
+    const int ts = ts_begin(TSK_LN);
     pdl_wait();
+    ts_dep(ts);
     __shared__ float red[8];
     __shared__ float stat[2];
     const int m = blockIdx.x;
@@ -127,6 +131,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
         const int d = threadIdx.x + i * 256;
         if (d < D) o[d] = from_f32<TO>((v[i] - mean) * rstd * w[d] + b[d]);
     }
+    ts_end(ts);
 }
 
 int launch_layernorm(const float* x, const int* idx, int M, int D, const float* w, const float* b, void* out,
@@ -518,7 +523,9 @@ __global__ void __launch_bounds__(256) sample_kernel(const float* __restrict__ l
                                                      int* __restrict__ gen_tok, const float* __restrict__ noise,
                                                      int* __restrict__ iter_counter, SampleParams p) {
     pdl_launch_dependents();
+    const int ts = ts_begin(TSK_SAMPLE);
     pdl_wait();
+    ts_dep(ts);
     __shared__ GroupRed red;
     __shared__ int s_samples[4];
     __shared__ int s_argmax0;
@@ -685,6 +692,7 @@ __global__ void __launch_bounds__(256) sample_kernel(const float* __restrict__ l
     N.y_len = S.y_len + 1;
     for (int j = 0; j < p.rpu; j++) seq_len[row0 + j] += 1;
     st[u] = N;
+    ts_end(ts);
 }
 
 int launch_sample(const float* logits, UttState* st, int* seq_len, int* next_tok, int* gen_tok, const float* noise,
@@ -694,5 +702,7 @@ int launch_sample(const float* logits, UttState* st, int* seq_len, int* next_tok
     SSRB_LAUNCH_PDL(sample_kernel, p.n_utt, 256, 0, s, logits, st, seq_len, next_tok, gen_tok, noise, iter_counter, p);
     return 0;
 }
+
+int ts_arm_lm_kernels(const TsBuf& t) { return ts_arm_tu(t); }
 
 }  // namespace ssrb
