@@ -234,14 +234,16 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ Tm
 #pragma unroll 1
                 for (int c0 = 0; c0 < QROWS; c0 += 16) {
                     if (c0 >= prm.M) break;
-                    float v[16];
+                    float v[16], resv[16];
                     tmem_ld16(taddr + c0, v);
+#pragma unroll
+                    for (int j = 0; j < 16; j++)          // all residual loads of the chunk in flight before the first store
+                        resv[j] = (prm.residual && nok && c0 + j < prm.M) ? __ldcg(prm.residual + (long long)(c0 + j) * prm.ldr + n) : 0.f;
 #pragma unroll
                     for (int j = 0; j < 16; j++) {
                         const int r = c0 + j;
                         if (r < prm.M && nok) {
-                            float x = apply_act(v[j] + bv, prm.act);
-                            if (prm.residual) x += prm.residual[(long long)r * prm.ldr + n];
+                            const float x = apply_act(v[j] + bv, prm.act) + resv[j];
                             const long long o = grp * prm.c_gs + (long long)r * prm.ldc + n;
                             if (prm.c_dtype == SSRB_DTYPE_F32) reinterpret_cast<float*>(prm.C)[o] = x;
                             else reinterpret_cast<bf16*>(prm.C)[o] = __float2bfloat16_rn(x);
@@ -316,16 +318,40 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ Tm
             const int n = p_row0 + nl;
             if (n < prm.N) {
                 const float bv = prm.bias ? prm.bias[grp * prm.bias_gs + n] : 0.f;
-                for (int r = (int)rank; r < prm.M; r += prm.splits) {     // interleaved rows: balanced for any M
-                    const uint32_t la = base + (uint32_t)((r * 128 + nl) * 4);
-                    float acc = 0.f;
-#pragma unroll 8
-                    for (int s = 0; s < prm.splits; s++) acc += ld_dsmem(la, (uint32_t)s);    // fixed order
-                    float x = apply_act(acc + bv, prm.act);
-                    if (prm.residual) x += prm.residual[(long long)r * prm.ldr + n];
-                    const long long o = grp * prm.c_gs + (long long)r * prm.ldc + n;
-                    if (prm.c_dtype == SSRB_DTYPE_F32) reinterpret_cast<float*>(prm.C)[o] = x;
-                    else reinterpret_cast<bf16*>(prm.C)[o] = __float2bfloat16_rn(x);
+                uint32_t rbase[MAX_SPLITS];                                // this CTA's tile address inside every peer
+#pragma unroll
+                for (int s = 0; s < MAX_SPLITS; s++)
+                    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbase[s]) : "r"(base), "r"((uint32_t)(s < prm.splits ? s : 0)));
+                // rows rank, rank+S, ... (interleaved: balanced for any M), 8 at a time: all residual and DSMEM loads of a
+                // batch are issued before the first store, so their latencies overlap instead of adding up per row
+                for (int r0 = (int)rank; r0 < prm.M; r0 += 8 * prm.splits) {
+                    float resv[8], part[MAX_SPLITS][8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const int r = r0 + j * prm.splits;
+                        resv[j] = (prm.residual && r < prm.M) ? __ldcg(prm.residual + (long long)r * prm.ldr + n) : 0.f;
+                    }
+#pragma unroll
+                    for (int s = 0; s < MAX_SPLITS; s++)
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            const int r = r0 + j * prm.splits;
+                            part[s][j] = 0.f;
+                            if (s < prm.splits && r < prm.M)
+                                asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(part[s][j]) : "r"(rbase[s] + (uint32_t)((r * 128 + nl) * 4)) : "memory");
+                        }
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const int r = r0 + j * prm.splits;
+                        if (r >= prm.M) continue;
+                        float acc = 0.f;
+#pragma unroll
+                        for (int s = 0; s < MAX_SPLITS; s++) acc += part[s][j];       // fixed order: deterministic
+                        const float x = apply_act(acc + bv, prm.act) + resv[j];
+                        const long long o = grp * prm.c_gs + (long long)r * prm.ldc + n;
+                        if (prm.c_dtype == SSRB_DTYPE_F32) reinterpret_cast<float*>(prm.C)[o] = x;
+                        else reinterpret_cast<bf16*>(prm.C)[o] = __float2bfloat16_rn(x);
+                    }
                 }
             }
         }
@@ -378,8 +404,9 @@ int qrows_for(int M) { return M <= 16 ? 16 : (M <= 32 ? 32 : (M <= 64 ? 64 : 128
 // split-K factor: a power of two <= 8 (cluster size) that divides the k-blocks, >= 4 k-blocks per CTA, enough CTAs to cover
 // the 148 SMs once (each CTA keeps 4 x 24 KB of TMA loads in flight, which is what saturates HBM — not the CTA count)
 int pick_splits(int tiles, int nkb) {
+    static const int target = [] { const char* e = getenv("SSRB_SPLIT_TARGET"); return e ? atoi(e) : 148; }();
     int s = 1;
-    while (s * 2 <= MAX_SPLITS && nkb % (s * 2) == 0 && nkb / (s * 2) >= 4 && tiles * s < 148) s *= 2;
+    while (s * 2 <= MAX_SPLITS && nkb % (s * 2) == 0 && nkb / (s * 2) >= 4 && tiles * s < target) s *= 2;
     return s;
 }
 
