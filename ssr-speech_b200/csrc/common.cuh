@@ -80,7 +80,7 @@ int launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cud
 }
 
 // ---- poor man's timeline (no nsys in this image): when armed (ssrb_debug_timeline), thread 0 of every CTA of the decode-chain
-// kernels records {kernel id, linear CTA id, globaltimer at entry, after griddepcontrol.wait, at exit, aux}; tools/timeline.py reconstructs the
+// kernels records of 10 u64 {kernel id, linear CTA id, entry, after griddepcontrol.wait, exit, aux0..aux4}; tools/timeline.py reconstructs the
 // overlap between kernels of the PDL chain from the dump.
 struct TsBuf { unsigned long long* buf; unsigned int* idx; unsigned int cap; };
 static __device__ TsBuf g_ts = {nullptr, nullptr, 0};      // one copy per translation unit (no -rdc); armed by ts_arm_tu()
@@ -95,15 +95,15 @@ __device__ __forceinline__ int ts_begin(int kernel_id) {
     if (g_ts.buf == nullptr || threadIdx.x != 0 || threadIdx.y != 0) return -1;
     const unsigned int slot = atomicAdd(g_ts.idx, 1u);
     if (slot >= g_ts.cap) return -1;
-    g_ts.buf[slot * 6 + 0] = (unsigned long long)kernel_id;
-    g_ts.buf[slot * 6 + 1] = (unsigned long long)(blockIdx.x + gridDim.x * (blockIdx.y + (unsigned long long)gridDim.y * blockIdx.z));
-    g_ts.buf[slot * 6 + 2] = globaltimer_ns();
-    g_ts.buf[slot * 6 + 3] = 0; g_ts.buf[slot * 6 + 4] = 0; g_ts.buf[slot * 6 + 5] = 0;
+    g_ts.buf[slot * 10 + 0] = (unsigned long long)kernel_id;
+    g_ts.buf[slot * 10 + 1] = (unsigned long long)(blockIdx.x + gridDim.x * (blockIdx.y + (unsigned long long)gridDim.y * blockIdx.z));
+    g_ts.buf[slot * 10 + 2] = globaltimer_ns();
+    for (int i = 3; i < 10; i++) g_ts.buf[slot * 10 + i] = 0;
     return (int)slot;
 }
-__device__ __forceinline__ void ts_dep(int slot) { if (slot >= 0) g_ts.buf[slot * 6 + 3] = globaltimer_ns(); }
-__device__ __forceinline__ void ts_aux(int slot) { if (slot >= 0) g_ts.buf[slot * 6 + 5] = globaltimer_ns(); }
-__device__ __forceinline__ void ts_end(int slot) { if (slot >= 0) g_ts.buf[slot * 6 + 4] = globaltimer_ns(); }
+__device__ __forceinline__ void ts_dep(int slot) { if (slot >= 0) g_ts.buf[slot * 10 + 3] = globaltimer_ns(); }
+__device__ __forceinline__ void ts_aux(int slot, int i = 0) { if (slot >= 0) g_ts.buf[slot * 10 + 5 + i] = globaltimer_ns(); }
+__device__ __forceinline__ void ts_end(int slot) { if (slot >= 0) g_ts.buf[slot * 10 + 4] = globaltimer_ns(); }
 enum TsKernel { TSK_EMBED = 1, TSK_LN = 2, TSK_GEMM = 3, TSK_ATTN = 4, TSK_SAMPLE = 5 };
 
 // launch of a kernel that belongs to a PDL chain (the kernel itself calls pdl_launch_dependents()/pdl_wait())

@@ -131,7 +131,9 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ Tm
     const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 1);
 
     pdl_launch_dependents();
+    __shared__ int s_ts;
     const int ts = ts_begin(TSK_GEMM);
+    if (threadIdx.x == 0) s_ts = ts;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int grp = blockIdx.z;
     int p_row0, q_row0, kb0, kb1;
@@ -226,6 +228,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ Tm
             mbar_wait(accum_bar, 0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
+        if (threadIdx.x == 64) ts_aux(s_ts, 1);           // accumulators complete
         if (SWAP) {
             const int n = p_row0 + nl;
             const bool nok = n < prm.N;
@@ -312,49 +315,67 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ Tm
     __syncwarp();                                             // reconverge the single-lane producer / MMA warps
     if (clustered) {
         // ===== split-K reduction across the cluster through distributed shared memory =====
+        if (threadIdx.x == 64) ts_aux(s_ts, 2);           // partial tile parked
         cluster_sync_all();                                 // every CTA's partial tile is parked and visible
+        if (threadIdx.x == 64) ts_aux(s_ts, 3);           // cluster barrier passed
         if (warp >= 2) {
+            // Reduce-scatter with 16-byte DSMEM accesses: this CTA owns rows rank, rank+S, ...; each epilogue warp takes
+            // every 4th of them and each lane 4 consecutive output features, so one row of one peer is ONE 512-byte warp
+            // request (the DSMEM path is request-bound: scalar 4-byte lanes were 5 us per GEMM, see profiles/).
             const uint32_t rank = cluster_ctarank();
-            const int n = p_row0 + nl;
-            if (n < prm.N) {
-                const float bv = prm.bias ? prm.bias[grp * prm.bias_gs + n] : 0.f;
+            const int ew = warp - 2;
+            const int n = p_row0 + 4 * lane;
+            if (n < prm.N) {                                              // N % 4 == 0 (checked on the host)
+                float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (prm.bias) bv = *reinterpret_cast<const float4*>(prm.bias + grp * prm.bias_gs + n);
                 uint32_t rbase[MAX_SPLITS];                                // this CTA's tile address inside every peer
 #pragma unroll
                 for (int s = 0; s < MAX_SPLITS; s++)
                     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbase[s]) : "r"(base), "r"((uint32_t)(s < prm.splits ? s : 0)));
-                // rows rank, rank+S, ... (interleaved: balanced for any M), 8 at a time: all residual and DSMEM loads of a
-                // batch are issued before the first store, so their latencies overlap instead of adding up per row
-                for (int r0 = (int)rank; r0 < prm.M; r0 += 8 * prm.splits) {
-                    float resv[8], part[MAX_SPLITS][8];
+                // 4 rows per batch: all residual and DSMEM loads of a batch are issued before its first store
+                for (int r0 = (int)rank + ew * prm.splits; r0 < prm.M; r0 += 16 * prm.splits) {
+                    float4 resv[4], part[MAX_SPLITS][4];
 #pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        const int r = r0 + j * prm.splits;
-                        resv[j] = (prm.residual && r < prm.M) ? __ldcg(prm.residual + (long long)r * prm.ldr + n) : 0.f;
+                    for (int j = 0; j < 4; j++) {
+                        const int r = r0 + j * 4 * prm.splits;
+                        resv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (prm.residual && r < prm.M) resv[j] = __ldcg(reinterpret_cast<const float4*>(prm.residual + (long long)r * prm.ldr + n));
                     }
 #pragma unroll
                     for (int s = 0; s < MAX_SPLITS; s++)
 #pragma unroll
-                        for (int j = 0; j < 8; j++) {
-                            const int r = r0 + j * prm.splits;
-                            part[s][j] = 0.f;
+                        for (int j = 0; j < 4; j++) {
+                            const int r = r0 + j * 4 * prm.splits;
+                            part[s][j] = make_float4(0.f, 0.f, 0.f, 0.f);
                             if (s < prm.splits && r < prm.M)
-                                asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(part[s][j]) : "r"(rbase[s] + (uint32_t)((r * 128 + nl) * 4)) : "memory");
+                                asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];"
+                                             : "=f"(part[s][j].x), "=f"(part[s][j].y), "=f"(part[s][j].z), "=f"(part[s][j].w)
+                                             : "r"(rbase[s] + (uint32_t)((r * 128 + 4 * lane) * 4)) : "memory");
                         }
 #pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        const int r = r0 + j * prm.splits;
+                    for (int j = 0; j < 4; j++) {
+                        const int r = r0 + j * 4 * prm.splits;
                         if (r >= prm.M) continue;
-                        float acc = 0.f;
+                        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                        for (int s = 0; s < MAX_SPLITS; s++) acc += part[s][j];       // fixed order: deterministic
-                        const float x = apply_act(acc + bv, prm.act) + resv[j];
+                        for (int s = 0; s < MAX_SPLITS; s++) {                 // fixed order: deterministic
+                            acc.x += part[s][j].x; acc.y += part[s][j].y; acc.z += part[s][j].z; acc.w += part[s][j].w;
+                        }
+                        float4 x;
+                        x.x = apply_act(acc.x + bv.x, prm.act) + resv[j].x; x.y = apply_act(acc.y + bv.y, prm.act) + resv[j].y;
+                        x.z = apply_act(acc.z + bv.z, prm.act) + resv[j].z; x.w = apply_act(acc.w + bv.w, prm.act) + resv[j].w;
                         const long long o = grp * prm.c_gs + (long long)r * prm.ldc + n;
-                        if (prm.c_dtype == SSRB_DTYPE_F32) reinterpret_cast<float*>(prm.C)[o] = x;
-                        else reinterpret_cast<bf16*>(prm.C)[o] = __float2bfloat16_rn(x);
+                        if (prm.c_dtype == SSRB_DTYPE_F32) *reinterpret_cast<float4*>(reinterpret_cast<float*>(prm.C) + o) = x;
+                        else {
+                            __nv_bfloat162 lo = __floats2bfloat162_rn(x.x, x.y), hi = __floats2bfloat162_rn(x.z, x.w);
+                            uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&lo); pk.y = *reinterpret_cast<uint32_t*>(&hi);
+                            *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(prm.C) + o) = pk;
+                        }
                     }
                 }
             }
         }
+        if (threadIdx.x == 64) ts_aux(s_ts, 4);           // reduce + store done
         cluster_sync_all();                                   // peers may still be reading this CTA's smem
     } else {
         __syncthreads();
@@ -449,6 +470,7 @@ int gemm_tc(const GemmArgs& g, void*, size_t, cudaStream_t s) {
         const int q = qrows_for(g.M);
         const int tiles = cdiv(g.N, P_ROWS);
         prm.splits = pick_splits(tiles * g.groups, prm.nkb);
+        if (g.N % 4 != 0 || g.ldc % 4 != 0 || g.c_gs % 4 != 0 || (g.residual && g.ldr % 4 != 0) || g.bias_gs % 4 != 0) prm.splits = 1;   // vector epilogue
         prm.kb_per_split = prm.nkb / prm.splits;
         for (int i = 0; i < g.groups; i++) {
             SSRB_TRY(make_map(&maps.g[i].p, W + i * g.w_gs, g.N, g.K, g.ldw, P_ROWS));

@@ -35,14 +35,14 @@ def main():
     _lib.check(lib.ssrb_lm_decode(m._h, args.skip, st), "decode")
     torch.cuda.synchronize()
     cap = 400000
-    buf = torch.zeros(cap * 6, dtype=torch.int64, device="cuda")
+    buf = torch.zeros(cap * 10, dtype=torch.int64, device="cuda")
     idx = torch.zeros(1, dtype=torch.int32, device="cuda")
     _lib.check(lib.ssrb_debug_timeline(C.c_void_p(buf.data_ptr()), C.c_void_p(idx.data_ptr()), cap), "timeline")
     _lib.check(lib.ssrb_lm_decode(m._h, args.iters, st), "decode")
     torch.cuda.synchronize()
     _lib.check(lib.ssrb_debug_timeline(None, None, 0), "timeline")
     n = int(idx.item())
-    rec = buf[:n * 6].view(n, 6).cpu().numpy()
+    rec = buf[:n * 10].view(n, 10).cpu().numpy()
     np.save(args.out, rec)
     names = {1: "embed", 2: "ln", 3: "gemm", 4: "attn", 5: "sample"}
     t0 = rec[:, 2].min()
@@ -64,6 +64,16 @@ def main():
         gap = "" if prev_end is None else f" gap_after_prev_end={s0 - prev_end:7.2f}"
         print(f"{gi:3d} {names.get(int(r[0, 0]), '?'):6s} ctas={len(gidx):5d} start={s0:9.2f} dep={dep:9.2f} end={e1:9.2f} dur={e1 - s0:7.2f}{gap}")
         prev_end = e1
+    # GEMM phase breakdown (medians over CTAs, us): dep->loads issued->accum ready->parked->cluster barrier->reduced->exit
+    g = rec[rec[:, 0] == 3]
+    g = g[np.argsort(g[:, 3])]
+    cuts = np.where(np.diff(g[:, 3]) > 3000)[0] + 1
+    for li, idxs in enumerate(np.split(np.arange(len(g)), cuts)[8:24]):
+        r = g[idxs].astype(np.float64)
+        med = lambda a: float(np.median(a)) / 1e3
+        d = r[:, 3]
+        print(f"gemm#{li} ctas={len(r):4d} start-dep={med(r[:,2]-d):7.2f} loads_issued={med(r[:,5]-d):6.2f} accum={med(r[:,6]-d):6.2f} "
+              f"parked={med(r[:,7]-d):6.2f} cbar={med(r[:,8]-d):6.2f} reduced={med(r[:,9]-d):6.2f} exit={med(r[:,4]-d):6.2f} (max exit {float((r[:,4]-d).max())/1e3:6.2f})")
 
 
 if __name__ == "__main__":
