@@ -120,7 +120,7 @@ template <int QROWS> struct TcCfg {
 };
 
 template <int QROWS, bool SWAP>
-__global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ TmaGroup maps, const TcParams prm) {
+__global__ void __launch_bounds__(192, 2) gemm_tc_kernel(const __grid_constant__ TmaGroup maps, const TcParams prm) {
     using Cfg = TcCfg<QROWS>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B tiles need 1024 B alignment
@@ -332,35 +332,42 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ Tm
 #pragma unroll
                 for (int s = 0; s < MAX_SPLITS; s++)
                     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbase[s]) : "r"(base), "r"((uint32_t)(s < prm.splits ? s : 0)));
-                // 4 rows per batch: all residual and DSMEM loads of a batch are issued before its first store
-                for (int r0 = (int)rank + ew * prm.splits; r0 < prm.M; r0 += 16 * prm.splits) {
-                    float4 resv[4], part[MAX_SPLITS][4];
+                // 2 rows per batch: all residual and DSMEM loads of a batch are issued before its first store
+                for (int r0 = (int)rank + ew * prm.splits; r0 < prm.M; r0 += 8 * prm.splits) {
+                    float4 resv[2], acc4[2];
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
+                    for (int j = 0; j < 2; j++) {
                         const int r = r0 + j * 4 * prm.splits;
                         resv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        acc4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (prm.residual && r < prm.M) resv[j] = __ldcg(reinterpret_cast<const float4*>(prm.residual + (long long)r * prm.ldr + n));
                     }
 #pragma unroll
-                    for (int s = 0; s < MAX_SPLITS; s++)
+                    for (int sh = 0; sh < MAX_SPLITS; sh += 4) {               // 8 vector loads in flight per lane, bounded registers
+                        float4 part[4][2];
 #pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            const int r = r0 + j * 4 * prm.splits;
-                            part[s][j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (s < prm.splits && r < prm.M)
-                                asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];"
-                                             : "=f"(part[s][j].x), "=f"(part[s][j].y), "=f"(part[s][j].z), "=f"(part[s][j].w)
-                                             : "r"(rbase[s] + (uint32_t)((r * 128 + 4 * lane) * 4)) : "memory");
-                        }
+                        for (int s = 0; s < 4; s++)
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
+                            for (int j = 0; j < 2; j++) {
+                                const int r = r0 + j * 4 * prm.splits;
+                                part[s][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (sh + s < prm.splits && r < prm.M)
+                                    asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];"
+                                                 : "=f"(part[s][j].x), "=f"(part[s][j].y), "=f"(part[s][j].z), "=f"(part[s][j].w)
+                                                 : "r"(rbase[sh + s] + (uint32_t)((r * 128 + 4 * lane) * 4)) : "memory");
+                            }
+#pragma unroll
+                        for (int s = 0; s < 4; s++)                             // fixed order: deterministic
+#pragma unroll
+                            for (int j = 0; j < 2; j++) {
+                                acc4[j].x += part[s][j].x; acc4[j].y += part[s][j].y; acc4[j].z += part[s][j].z; acc4[j].w += part[s][j].w;
+                            }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 2; j++) {
                         const int r = r0 + j * 4 * prm.splits;
                         if (r >= prm.M) continue;
-                        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                        for (int s = 0; s < MAX_SPLITS; s++) {                 // fixed order: deterministic
-                            acc.x += part[s][j].x; acc.y += part[s][j].y; acc.z += part[s][j].z; acc.w += part[s][j].w;
-                        }
+                        const float4 acc = acc4[j];
                         float4 x;
                         x.x = apply_act(acc.x + bv.x, prm.act) + resv[j].x; x.y = apply_act(acc.y + bv.y, prm.act) + resv[j].y;
                         x.z = apply_act(acc.z + bv.z, prm.act) + resv[j].z; x.w = apply_act(acc.w + bv.w, prm.act) + resv[j].w;
