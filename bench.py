@@ -185,12 +185,22 @@ def cpu_reference_sample(args, n_iters: int):
             if dt < best[1]:
                 best = (nt, dt)
         torch.set_num_threads(best[0])
-        t0 = time.perf_counter()
-        oracle.inference(x, torch.from_numpy(prep.prompt_tokens), 1, max_steps=1, **kw)
-        t_prefill = time.perf_counter() - t0
+        # one bounded run; the prediction heads are evaluated once per row per iteration, so their call times mark the
+        # iteration boundaries (row 0 and row 1 of the CFG pair)
+        stamps = []
+        orig_heads = oracle.heads
+
+        def heads_timed(hvec):
+            out = orig_heads(hvec)
+            stamps.append(time.perf_counter())
+            return out
+        oracle.heads = heads_timed
         t0 = time.perf_counter()
         oracle.inference(x, torch.from_numpy(prep.prompt_tokens), 1, max_steps=1 + n_iters, **kw)
-        t_iter = (time.perf_counter() - t0 - t_prefill) / n_iters
+        oracle.heads = orig_heads
+        R = 2
+        t_prefill = stamps[R - 1] - t0
+        t_iter = (stamps[-1] - stamps[R - 1]) / max(len(stamps) // R - 1, 1)
     t_codec = cpu_codec_seconds(args, T, gen_frames)
     t_utt = t_codec + t_prefill + (n_total - 1) * t_iter
     tokens = K_CODEBOOKS * gen_frames
@@ -459,23 +469,24 @@ def main():
 
 
 def profile_breakdown(model, lib, texts, ys, spans, dc, args, gen_frames):
-    """Per-kernel-class time of one decode iteration near mid-generation (un-graphed; CUDA events per class) and the
-    HBM rate of the two streaming classes: attention (KV bytes) and the GEMMs (weight bytes)."""
-    import ctypes as C
-    from ssr_speech_b200 import _lib
+    """Critical-path decomposition of one decode iteration near mid-generation, measured INSIDE the CUDA-graph / PDL chain with
+    in-kernel %globaltimer stamps (ssr_speech_b200.timeline): per kernel class, the sum over its launches of
+    max(CTA exit) - min(dependency resolved).  HBM rates: attention over the KV bytes, GEMMs over the weight bytes."""
+    from ssr_speech_b200 import _lib, timeline
     half = gen_frames // 2
     model.open_batch(texts, ys, spans, top_k=dc["top_k"], top_p=dc["top_p"], temperature=dc["temperature"],
                      stop_repetition=dc["stop_repetition"], cfg_coef=1.5, cfg_stride=5, aug_text=True, seed=1000)
     st = _lib.stream_ptr()
     _lib.check(lib.ssrb_lm_decode(model._h, half, st), "decode")
-    cls = (C.c_double * 4)()
-    tot = C.c_double(0)
-    _lib.check(lib.ssrb_lm_profile_steps(model._h, args.profile_iters, st, cls, C.byref(tot)), "profile")
     wb, kb = model.step_bytes()
-    out = {"at_iteration": half, "ms_per_iteration_ungraphed": tot.value,
-           "attention_ms": cls[0], "gemm_ms": cls[1], "ln_embed_kvappend_ms": cls[2], "sample_ms": cls[3],
-           "attention_GBps": kb / (cls[0] / 1e3) / 1e9 if cls[0] else None,
-           "gemm_GBps": wb / (cls[1] / 1e3) / 1e9 if cls[1] else None, "kv_bytes": kb, "weight_bytes": wb}
+    n = max(2, args.profile_iters)
+    cp = timeline.critical_path(timeline.capture(model, n), n)
+    out = {"at_iteration": half, "method": "in-kernel globaltimer stamps under the CUDA graph (critical path per class)",
+           "iteration_us": cp["wall_us"], "attention_us": cp["attention_us"], "gemm_us": cp["gemm_us"],
+           "layernorm_us": cp["layernorm_us"], "embed_us": cp["embed_us"], "sample_us": cp["sample_us"],
+           "gemm_launches": cp["gemm_launches"], "attention_launches": cp["attention_launches"],
+           "attention_GBps": kb / (cp["attention_us"] * 1e-6) / 1e9 if cp["attention_us"] else None,
+           "gemm_GBps": wb / (cp["gemm_us"] * 1e-6) / 1e9 if cp["gemm_us"] else None, "kv_bytes": kb, "weight_bytes": wb}
     _lib.check(lib.ssrb_lm_decode(model._h, gen_frames, st), "decode")   # drain
     torch.cuda.synchronize()
     return out

@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(256) embed_step_kernel(const int* __restrict__
         float e = __fadd_rn(__fadd_rn(__fadd_rn(e0[d], e1[d]), e2[d]), e3[d]);
         xo[d] = __fadd_rn(e, __fmul_rn(alpha_a, per[d]));
     }
+    ts_end(ts);
 }
 
 int launch_embed_prefill(const PosDesc* desc, int M, int D, const float* text_emb, const float* audio_emb, int V,
