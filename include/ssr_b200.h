@@ -175,6 +175,11 @@ int ssrb_codec_decode(ssrb_codec* c, const int64_t* codes_dev, int B, int Tf, fl
 int ssrb_codec_wmdecode(ssrb_codec* c, const int64_t* codes_dev, const int64_t* marks_dev, const float* wav_in_dev,
                         int B, int Tf, float* wav_out_dev, float* mark_logits_dev, void* stream);
 
+/* WMEncodecModel.detect_watermark (wmencodec.py:377-382): wav fp32 [B,1,T] -> per-frame watermark logits fp32 [B,T/hop,2]
+ * = wm_predictor(wm_encoder(wav)).  (The reference then takes argmax over the TIME axis, a bug — SURVEY §0; the Python
+ * mirror exposes both behaviours.) */
+int ssrb_codec_detect_watermark(ssrb_codec* c, const float* wav_dev, int B, int T, float* mark_logits_dev, void* stream);
+
 /* Debug: arms (dev_buf != NULL) or disarms the in-kernel timeline of the decode-chain kernels.  dev_buf holds cap x 4 u64
  * records {kernel id, CTA id, globaltimer ns at entry, at exit}; *dev_idx counts records (tools/timeline.py). */
 int ssrb_debug_timeline(unsigned long long* dev_buf, unsigned int* dev_idx, unsigned int cap);

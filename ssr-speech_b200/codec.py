@@ -157,6 +157,26 @@ class WMEncodecModel:
         return out, marks
 
 
+def _detect_watermark(self, x: torch.Tensor, reference_axis_bug: bool = True):
+    """WMEncodecModel.detect_watermark (wmencodec.py:377-382).  Returns (marks, logits [B,Tf,2]).
+    reference_axis_bug=True reproduces the reference exactly: argmax over dim=-1 of logits laid out [B,2,Tf] (i.e. over TIME,
+    shape [B,2]); False returns the per-frame class decision [B,Tf] the code evidently intended."""
+    assert x.dim() == 3
+    h = self._engine()
+    x = x.to(self._device, torch.float32).contiguous()
+    B, _, T = x.shape
+    Tf = T // self.cfg.hop_length
+    logits = torch.empty(B, Tf, 2, dtype=torch.float32, device=self._device)
+    with torch.cuda.device(self._device):
+        _lib.check(_lib.load().ssrb_codec_detect_watermark(h, C.c_void_p(x.data_ptr()), B, T, C.c_void_p(logits.data_ptr()),
+                                                           _lib.stream_ptr()), "codec_detect_watermark")
+    marks = torch.argmax(logits.transpose(1, 2), dim=-1) if reference_axis_bug else torch.argmax(logits, dim=-1)
+    return marks, logits
+
+
+WMEncodecModel.detect_watermark = _detect_watermark
+
+
 def _cfg_from_xp(xp_cfg) -> CodecConfig:
     """Best-effort read of the resolved Hydra cfg stored in the checkpoint (wmcompression.py:302-304)."""
     def get(o, k, d=None):
@@ -212,6 +232,10 @@ class AudioTokenizer:
         out, _ = self.codec.wmdecode(frames.to(self.device), marks.to(self.device), wav.to(self.device), scale,
                                      return_marks=False)
         return out
+
+    def detect_watermark(self, wav: torch.Tensor):
+        marks, _ = self.codec.detect_watermark(wav.to(self.device))
+        return marks
 
 
 def load_wav(path: str, offset: int = -1, num_frames: int = -1):

@@ -653,3 +653,25 @@ int ssrb_codec_wmdecode(ssrb_codec* c, const int64_t* codes, const int64_t* mark
     }
     return 0;
 }
+
+// WMEncodecModel.detect_watermark (wmencodec.py:377-382): m = wm_predictor(wm_encoder(x)) -> logits [B,Tf,2] (fp32 path).
+int ssrb_codec_detect_watermark(ssrb_codec* c, const float* wav, int B, int T, float* mark_logits, void* stream) {
+    SSRB_CHECK(c && wav && mark_logits, "null argument");
+    SSRB_CHECK(T > 0 && T % c->hop == 0, "detect_watermark: T must be a positive multiple of the hop length");
+    SSRB_CUDA(cudaSetDevice(c->device));
+    SSRB_TRY(ssrb_codec_check_loaded(c));
+    cudaStream_t s = (cudaStream_t)stream;
+    const int Tf = T / c->hop;
+    for (int b0 = 0; b0 < B; b0 += c->cfg.max_batch_chunk) {
+        const int nb = std::min(c->cfg.max_batch_chunk, B - b0);
+        SSRB_TRY(run_planned(c, [&]() -> int {
+            Ctx x{c, s, nb};
+            Tensor in{const_cast<float*>(wav) + (size_t)b0 * T, 1, T}, m, mp;
+            SSRB_TRY(encoder(x, "wmdecoder.wm_encoder.", in, &m));
+            SSRB_TRY(conv(x, "wmdecoder.wm_predictor.1.conv.conv.", m, 1, true, nullptr, &mp));
+            if (c->arena.dry) return 0;
+            return launch_bct_to_btc(mp.p, nb, 2, Tf, mark_logits + (size_t)b0 * Tf * 2, s);
+        }));
+    }
+    return 0;
+}

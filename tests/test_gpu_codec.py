@@ -182,3 +182,17 @@ def test_tc_longer_ragged_batch_matches_fp32_path(small_tc):
     a, _ = m.wmdecode(codes, marks, wav, return_marks=False)
     b, _ = ref.wmdecode(codes, marks, wav, return_marks=False)
     assert (a - b).abs().max() <= TC_TOL * b.abs().max()
+
+
+def test_detect_watermark_matches_oracle_logits(small):
+    """§8(f)-3: watermark detector = wm_predictor(wm_encoder(x)); logits vs the oracle, plus the reference's argmax-over-time quirk."""
+    g, cfg, sd, m = small
+    o = CodecOracle(cfg, sd)
+    wav = torch.from_numpy(g["wav"])
+    want = o.conv(torch.nn.functional.elu(o.encoder(wav, "wmdecoder.wm_encoder.")), "wmdecoder.wm_predictor.1.conv.conv.").transpose(2, 1)
+    marks, logits = m.detect_watermark(wav.cuda())
+    assert (logits.cpu() - want).abs().max() <= 1e-4 * max(want.abs().max().item(), 1e-3)
+    assert tuple(marks.shape) == (2, 2)                     # the reference returns argmax over time: [B, 2] (SURVEY §0)
+    assert torch.equal(marks.cpu(), torch.argmax(want.transpose(1, 2), dim=-1))
+    per_frame, _ = m.detect_watermark(wav.cuda(), reference_axis_bug=False)
+    assert tuple(per_frame.shape) == (2, want.shape[1])
