@@ -103,7 +103,9 @@ class WMEncodecModel:
         x = x.to(self._device, torch.float32).contiguous()
         B, Cc, T = x.shape
         assert Cc == self.cfg.channels
-        Tf = T // self.cfg.hop_length
+        Tf = T
+        for r in reversed(self.cfg.ratios):        # ceil chain of the strided convs (= T // hop when hop divides T)
+            Tf = -(-Tf // r)
         codes = torch.empty(B, self.cfg.n_q, Tf, dtype=torch.int64, device=self._device)
         emb = torch.empty(B, self.cfg.dimension, Tf, dtype=torch.float32, device=self._device)
         with torch.cuda.device(self._device):

@@ -544,11 +544,14 @@ int ssrb_codec_quantize(ssrb_codec* c, const float* emb, int B, int Tf, int64_t*
 
 int ssrb_codec_encode(ssrb_codec* c, const float* wav, int B, int T, int64_t* codes, float* emb_out, void* stream) {
     SSRB_CHECK(c && wav && codes, "null argument");
-    SSRB_CHECK(T > 0 && T % c->hop == 0, "encode: T must be a positive multiple of the hop length");
+    SSRB_CHECK(T > 0, "encode: empty waveform");
     SSRB_CUDA(cudaSetDevice(c->device));
     SSRB_TRY(ssrb_codec_check_loaded(c));
     cudaStream_t s = (cudaStream_t)stream;
-    const int Tf = T / c->hop, Dm = c->cfg.dimension, nq = c->cfg.n_q;
+    // frames = ceil chain of the strided convs (StreamableConv1d pads the tail: conv.py:47-53); = T/hop when hop | T
+    int Tf = T;
+    for (int i = c->cfg.n_ratios - 1; i >= 0; i--) Tf = (Tf + c->cfg.ratios[i] - 1) / c->cfg.ratios[i];
+    const int Dm = c->cfg.dimension, nq = c->cfg.n_q;
     for (int b0 = 0; b0 < B; b0 += c->cfg.max_batch_chunk) {
         const int nb = std::min(c->cfg.max_batch_chunk, B - b0);
         SSRB_TRY(run_planned(c, [&]() -> int {

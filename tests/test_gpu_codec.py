@@ -196,3 +196,25 @@ def test_detect_watermark_matches_oracle_logits(small):
     assert torch.equal(marks.cpu(), torch.argmax(want.transpose(1, 2), dim=-1))
     per_frame, _ = m.detect_watermark(wav.cuda(), reference_axis_bug=False)
     assert tuple(per_frame.shape) == (2, want.shape[1])
+
+
+def test_dataset_encode_matches_reference_format(small, tmp_path):
+    """§8(f)-2 (data/encode.py): zero-padded ragged batch, non-multiple-of-320 lengths, txt format, frame cut."""
+    from ssr_speech_b200.encode_dataset import encode_items
+    g, cfg, sd, m = small
+    tok = AudioTokenizer(model=m, device="cuda")
+    gen = torch.Generator().manual_seed(11)
+    lens = [4000, 5317, 3210]
+    items = [{"segment_id": f"utt{i}", "wav": 0.1 * torch.randn(1, n, generator=gen)} for i, n in enumerate(lens)]
+    n = encode_items(tok, items, str(tmp_path), batch_size=8, model_sr=16000, code_sr=50)
+    assert n == 3
+    o = CodecOracle(cfg, sd)
+    padded = torch.nn.utils.rnn.pad_sequence([it["wav"].squeeze() for it in items], batch_first=True).unsqueeze(1)
+    want, _, emb = o.encode(padded)                                    # the reference pads, then encodes (encode.py:108-111)
+    assert want.shape[-1] == -(-5317 // 320)
+    for i, L in enumerate(lens):
+        rows = [list(map(int, ln.split())) for ln in open(tmp_path / f"utt{i}.txt").read().split("\n")]
+        assert len(rows) == 4 and all(len(r) == round(L / 16000 * 50) for r in rows)
+        got = np.asarray(rows)
+        ref = want[i, :, :got.shape[1]].numpy()
+        assert (got == ref).mean() >= 0.97
