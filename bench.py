@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--lx", type=int, default=101, help="phonemes per utterance (generation length = 10*lx - prompt frames - 9)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--codec-precision", default="bf16", choices=["bf16", "fp32"], help="decoder/wmdecode convolutions: bf16 tcgen05 or fp32 CUDA cores (encode is always fp32)")
+    ap.add_argument("--codec-chunk", type=int, default=32, help="utterances per codec pass (bounds the activation arena)")
     ap.add_argument("--no-watermark", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-iters", type=int, default=12)
@@ -318,7 +319,7 @@ def main():
     model.load_state_dict(make_lm_state_dict(cfg, seed=0, pin_eog_bias=True))
     model.to(dev).eval()
     ccfg = CodecConfig()
-    codec = WMEncodecModel(ccfg, max_batch_chunk=16, precision=args.codec_precision)
+    codec = WMEncodecModel(ccfg, max_batch_chunk=args.codec_chunk, precision=args.codec_precision)
     codec.load_state_dict(make_codec_state_dict(ccfg, seed=0))
     codec.to(dev)
     cal = 0.1 * torch.randn(4, 1, 32000, generator=torch.Generator().manual_seed(7))

@@ -123,4 +123,18 @@ int launch_cl_to_cf32(const bf16* in, int B, int C, int T, float* out, cudaStrea
     return 0;
 }
 
+// zero only the guard rows of a channels-last tensor (rows [0,T) are fully written by the producing epilogue)
+__global__ void cl_zero_guards_kernel(bf16* __restrict__ p, int T, int C) {
+    const int b = blockIdx.x, side = blockIdx.y;
+    bf16* g = p + ((int64_t)b * (T + 2 * CL_GUARD) + (side ? CL_GUARD + T : 0)) * C;
+    const int n = CL_GUARD * C;                               // multiple of 8
+    for (int e = threadIdx.x * 8; e < n; e += blockDim.x * 8) *reinterpret_cast<uint4*>(g + e) = make_uint4(0, 0, 0, 0);
+}
+int launch_cl_zero_guards(bf16* p, int B, int T, int C, cudaStream_t s) {
+    SSRB_CHECK(C % 8 == 0, "cl_zero_guards: C must be a multiple of 8");
+    dim3 grid(B, 2);
+    SSRB_LAUNCH(cl_zero_guards_kernel, grid, 256, 0, s, p, T, C);
+    return 0;
+}
+
 }  // namespace ssrb

@@ -27,6 +27,7 @@ struct TcW { bf16* w = nullptr; float* bias = nullptr; float* bias_alt = nullptr
 struct ClT { bf16* raw = nullptr; bf16* act = nullptr; int C = 0, T = 0; };   // channels-last tensor [B][G+T+G][C]
 struct LstmW {
     float *wih[4] = {}, *whh[4] = {}, *bsum[4] = {};
+    bf16* wih_bf16[4] = {};            // tensor-core input projection (decoder-side LSTMs only)
     std::vector<float> bih[4], bhh[4];
     bool has_wih[4] = {}, has_whh[4] = {}, has_b[4] = {};
     int C = 0;
@@ -235,33 +236,55 @@ static int resblock(Ctx& x, const std::string& prefix, Tensor in, Tensor* out) {
     SSRB_TRY(conv(x, prefix + "block.1.conv.conv.", in, 1, true, nullptr, &h));
     return conv(x, prefix + "block.3.conv.conv.", h, 1, true, in.p, out);
 }
-// StreamableLSTM (lstm.py:10-25)
-static int lstm(Ctx& x, const std::string& prefix, Tensor in, Tensor* out) {
+template <typename T>
+__global__ void f32_to_T_kernel(const float* __restrict__ src, T* __restrict__ dst, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = from_f32<T>(src[i]);
+}
+// StreamableLSTM (lstm.py:10-25).  tc: input projections x.W_ih^T as bf16 tcgen05 GEMMs (decoder-side LSTMs of the tensor-core path)
+static int lstm(Ctx& x, const std::string& prefix, Tensor in, Tensor* out, bool tc = false) {
     auto it = x.c->lstms.find(prefix);
     if (it == x.c->lstms.end()) { set_error("codec lstm missing: " + prefix); return 1; }
     LstmW& L = it->second;
     const int C = in.C, T = in.T, B = x.B, nl = x.c->cfg.lstm_layers;
     SSRB_CHECK(L.C == C, "lstm width mismatch");
+    tc = tc && (C % 64 == 0);
     Arena& A = x.c->arena;
     float* seq = A.f((size_t)T * B * C);
     float* pre = A.f((size_t)T * B * 4 * C);
     float* hs[2] = {A.f((size_t)T * B * C), A.f((size_t)T * B * C)};
     float* hbuf = A.f((size_t)2 * B * C);
+    bf16* seq16 = tc ? (bf16*)A.f(((size_t)T * B * C + 1) / 2) : nullptr;
+    bf16* hs16 = tc ? (bf16*)A.f(((size_t)T * B * C + 1) / 2) : nullptr;
     out->C = C; out->T = T; out->p = A.f((size_t)B * C * T);
     if (A.dry) return 0;
-    SSRB_TRY(launch_bct_to_tbc(in.p, B, C, T, seq, x.s));
+    SSRB_TRY(launch_bct_to_tbc(in.p, B, C, T, seq, x.s, seq16));
     const float* cur = seq;
+    const bf16* cur16 = seq16;
     for (int l = 0; l < nl; l++) {
         SSRB_CHECK(L.has_wih[l] && L.has_whh[l] && L.has_b[l], "lstm layer weights missing");
         GemmArgs g;
-        g.A = cur; g.lda = C; g.W = L.wih[l]; g.ldw = C; g.bias = L.bsum[l]; g.C = pre; g.ldc = 4 * C;
-        g.M = T * B; g.N = 4 * C; g.K = C; g.ab_dtype = SSRB_DTYPE_F32; g.c_dtype = SSRB_DTYPE_F32;
-        SSRB_TRY(gemm_simt(g, x.s));
-        SSRB_TRY(launch_lstm_layer(pre, L.whh[l], hs[l & 1], hbuf, x.c->bar, T, B, C, x.s));
+        g.bias = L.bsum[l]; g.C = pre; g.ldc = 4 * C; g.lda = C; g.ldw = C;
+        g.M = T * B; g.N = 4 * C; g.K = C; g.c_dtype = SSRB_DTYPE_F32;
+        if (tc) {
+            if (!L.wih_bf16[l]) {
+                SSRB_TRY(dalloc((void**)&L.wih_bf16[l], (size_t)4 * C * C * 2));
+                SSRB_LAUNCH(f32_to_T_kernel<bf16>, 512, 256, 0, x.s, L.wih[l], L.wih_bf16[l], (int64_t)4 * C * C);
+            }
+            g.A = cur16; g.W = L.wih_bf16[l]; g.ab_dtype = SSRB_DTYPE_BF16;
+            SSRB_TRY(gemm_tc(g, nullptr, 0, x.s));
+        } else {
+            g.A = cur; g.W = L.wih[l]; g.ab_dtype = SSRB_DTYPE_F32;
+            SSRB_TRY(gemm_simt(g, x.s));
+        }
+        SSRB_TRY(launch_lstm_layer(pre, L.whh[l], hs[l & 1], hbuf, x.c->bar, T, B, C, x.s, (tc && l + 1 < nl) ? hs16 : nullptr));
         cur = hs[l & 1];
+        cur16 = hs16;
     }
     return launch_tbc_to_bct_add(cur, in.p, B, C, T, out->p, x.s);
 }
+
+// frame-rate k7 convolution (128 <-> 1024 channels) through the tensor-core path: fp32 channels-first in and out
+static int conv_frame_tc(Ctx& x, const std::string& key, Tensor in, bool elu_in, const float* res, Tensor* out);
 
 // SEANetEncoder as the 5 slices WMSEANetDecoder.forward uses (seanet.py:559-574)
 static int encoder_stage(Ctx& x, const std::string& p, int stage, Tensor in, Tensor* out) {
@@ -402,9 +425,9 @@ static ClT cl_alloc(Ctx& x, int C, int T, bool raw, bool act) {
     const size_t n = (size_t)x.B * (T + 2 * CL_GUARD) * C;           // bf16 elements = n*2 bytes = n/2 floats
     if (raw) t.raw = (bf16*)x.c->arena.f((n + 1) / 2);
     if (act) t.act = (bf16*)x.c->arena.f((n + 1) / 2);
-    if (!x.c->arena.dry) {                                            // guards (and everything else) start as zeros
-        if (raw) cudaMemsetAsync(t.raw, 0, n * 2, x.s);
-        if (act) cudaMemsetAsync(t.act, 0, n * 2, x.s);
+    if (!x.c->arena.dry) {                                            // only the guard rows need zeroing: producers write every row
+        if (raw) launch_cl_zero_guards(t.raw, x.B, T, C, x.s);
+        if (act) launch_cl_zero_guards(t.act, x.B, T, C, x.s);
     }
     return t;
 }
@@ -444,6 +467,17 @@ static int tc_conv(Ctx& x, const std::string& key, int kind, int stride, const C
     if (residual) { a.res = residual; a.res_bstride = a.out_bstride; a.res_off = (long long)G * Cout; }
     if (x.c->arena.dry) return 0;
     return conv_tc(a, x.s);
+}
+static int conv_frame_tc(Ctx& x, const std::string& key, Tensor in, bool elu_in, const float* res, Tensor* out) {
+    const ConvW* W;
+    SSRB_TRY(get_conv(x.c, key, &W));
+    if (W->d0 % 64 != 0 || W->d1 % 64 != 0 || res) return conv(x, key, in, 1, elu_in, res, out);     // not tensor-core shaped
+    ClT a = cl_alloc(x, in.C, in.T, false, true), o;
+    if (!x.c->arena.dry) SSRB_TRY(launch_cf32_to_cl(in.p, x.B, in.C, in.T, elu_in, a.act, x.s));
+    SSRB_TRY(tc_conv(x, key, TC_CONV, 1, a, a.act, nullptr, true, false, nullptr, 0, 1, &o));
+    out->C = o.C; out->T = o.T; out->p = x.c->arena.f((size_t)x.B * o.C * o.T);
+    if (x.c->arena.dry) return 0;
+    return launch_cl_to_cf32(o.raw, x.B, o.C, o.T, out->p, x.s);
 }
 // SEANetResnetBlock on the tensor cores: y = x + conv_k1(ELU(conv_k3(ELU(x)))); only ELU(y) (and optionally y) is kept
 static int tc_resblock(Ctx& x, const std::string& prefix, const ClT& in, bool want_raw, ClT* out) {
@@ -502,8 +536,8 @@ static int skip_encoder_tc(Ctx& x, const std::string& p, const float* wav, int T
     SSRB_TRY(tc_conv(x, p + "model.12.conv.conv.", TC_CONVS, er[3], cur, cur.act, nullptr, true, false, nullptr, 0, 1, &d8));
     Tensor a{x.c->arena.f((size_t)x.B * d8.C * d8.T), d8.C, d8.T}, b;
     if (!x.c->arena.dry) SSRB_TRY(launch_cl_to_cf32(d8.raw, x.B, d8.C, d8.T, a.p, x.s));
-    if (x.c->cfg.lstm_layers > 0) { SSRB_TRY(lstm(x, p + "model.13.", a, &b)); } else b = a;
-    return conv(x, p + "model.15.conv.conv.", b, 1, true, nullptr, skip3);
+    if (x.c->cfg.lstm_layers > 0) { SSRB_TRY(lstm(x, p + "model.13.", a, &b, true)); } else b = a;
+    return conv_frame_tc(x, p + "model.15.conv.conv.", b, true, nullptr, skip3);
 }
 
 // runs `fn` twice: a dry pass to size the arena, then for real
@@ -584,8 +618,8 @@ int ssrb_codec_decode(ssrb_codec* c, const int64_t* codes, int B, int Tf, float*
                 SSRB_TRY(launch_rvq_decode((const long long*)codes + (size_t)b0 * nq * Tf, nb, nq, Tf, c->codebooks, c->cfg.bins, Dm, z.p, s));
             if (c->use_tc) {
                 Tensor a, b;
-                SSRB_TRY(conv(x, "decoder.model.0.conv.conv.", z, 1, false, nullptr, &a));
-                if (c->cfg.lstm_layers > 0) { SSRB_TRY(lstm(x, "decoder.model.1.", a, &b)); } else b = a;
+                SSRB_TRY(conv_frame_tc(x, "decoder.model.0.conv.conv.", z, false, nullptr, &a));
+                if (c->cfg.lstm_layers > 0) { SSRB_TRY(lstm(x, "decoder.model.1.", a, &b, true)); } else b = a;
                 return decoder_tail_tc(x, "decoder.", b, nullptr, nullptr, Tf, wav + (size_t)b0 * T);
             }
             SSRB_TRY(decoder(x, "decoder.", z, &out));
@@ -623,8 +657,8 @@ int ssrb_codec_wmdecode(ssrb_codec* c, const int64_t* codes, const int64_t* mark
                 cat.p = A.f((size_t)nb * (Dm + E) * Tf);
                 if (!A.dry) SSRB_TRY(launch_concat_marks(skip3.p, nb, Dm, Tf, mk, Tf, 1, c->wm_embed, E, cat.p, s));
                 SSRB_TRY(conv(x, "wmdecoder.wm_proj0.1.conv.conv.", cat, 1, true, lat.p, &o0));      // + x (seanet.py:577-578)
-                SSRB_TRY(conv(x, "wmdecoder.model.0.conv.conv.", o0, 1, false, nullptr, &a));
-                if (c->cfg.lstm_layers > 0) { SSRB_TRY(lstm(x, "wmdecoder.model.1.", a, &b)); } else b = a;
+                SSRB_TRY(conv_frame_tc(x, "wmdecoder.model.0.conv.conv.", o0, false, nullptr, &a));
+                if (c->cfg.lstm_layers > 0) { SSRB_TRY(lstm(x, "wmdecoder.model.1.", a, &b, true)); } else b = a;
                 return decoder_tail_tc(x, "wmdecoder.", b, sk, mk, Tf, wav_out + (size_t)b0 * T);
             }
             // skip encoder over the (partly zeroed) original waveform (seanet.py:559-574)

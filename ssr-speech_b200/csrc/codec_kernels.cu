@@ -242,7 +242,7 @@ int launch_convtr1d(const float* in, int B, int Cin, int Tin, const float* W, co
 // =================================================================================================
 // layout shuffles around the LSTM (modules/lstm.py:20-25: permute(2,0,1) ... + skip ... permute(1,2,0))
 // =================================================================================================
-__global__ void bct_to_tbc_kernel(const float* __restrict__ in, int B, int C, int T, float* __restrict__ out) {
+__global__ void bct_to_tbc_kernel(const float* __restrict__ in, int B, int C, int T, float* __restrict__ out, bf16* __restrict__ out_bf16) {
     __shared__ float tile[32][33];
     const int b = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
     for (int i = threadIdx.y; i < 32; i += 8) {
@@ -252,7 +252,10 @@ __global__ void bct_to_tbc_kernel(const float* __restrict__ in, int B, int C, in
     __syncthreads();
     for (int i = threadIdx.y; i < 32; i += 8) {
         const int t = t0 + i, c = c0 + threadIdx.x;
-        if (t < T && c < C) out[((int64_t)t * B + b) * C + c] = tile[threadIdx.x][i];
+        if (t < T && c < C) {
+            out[((int64_t)t * B + b) * C + c] = tile[threadIdx.x][i];
+            if (out_bf16) out_bf16[((int64_t)t * B + b) * C + c] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+        }
     }
 }
 __global__ void tbc_to_bct_add_kernel(const float* __restrict__ seq, const float* __restrict__ skip, int B, int C, int T,
@@ -272,9 +275,9 @@ __global__ void tbc_to_bct_add_kernel(const float* __restrict__ seq, const float
         }
     }
 }
-int launch_bct_to_tbc(const float* in, int B, int C, int T, float* out, cudaStream_t s) {
+int launch_bct_to_tbc(const float* in, int B, int C, int T, float* out, cudaStream_t s, bf16* out_bf16) {
     dim3 grid(cdiv(T, 32), cdiv(C, 32), B), block(32, 8);
-    SSRB_LAUNCH(bct_to_tbc_kernel, grid, block, 0, s, in, B, C, T, out);
+    SSRB_LAUNCH(bct_to_tbc_kernel, grid, block, 0, s, in, B, C, T, out, out_bf16);
     return 0;
 }
 int launch_tbc_to_bct_add(const float* seq, const float* skip, int B, int C, int T, float* out, cudaStream_t s) {
@@ -307,7 +310,7 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-
 
 __global__ void __launch_bounds__(256) lstm_layer_kernel(const float* __restrict__ pre, const float* __restrict__ Whh,
                                                          float* __restrict__ hseq, float* hbuf, unsigned int* bar,
-                                                         int T, int B, int C) {
+                                                         int T, int B, int C, bf16* __restrict__ hseq_bf16) {
     extern __shared__ __align__(16) float smem[];
     float* w_s = smem;                               // [32 rows = gate*8+unit][C]
     float* h_s = w_s + 4 * LSTM_UPB * C;             // [LSTM_BC][C]
@@ -389,6 +392,7 @@ __global__ void __launch_bounds__(256) lstm_layer_kernel(const float* __restrict
             const float hv = sigmoidf_(go) * tanhf(c_state);
             hnext[(size_t)cb * C + u0 + cu] = hv;
             hseq[((size_t)t * B + cb) * C + u0 + cu] = hv;
+            if (hseq_bf16) hseq_bf16[((size_t)t * B + cb) * C + u0 + cu] = __float2bfloat16_rn(hv);
             if (t + 1 < T) {                                  // input-projection terms of the next step: off the critical path
                 const float* pr = pre + ((size_t)(t + 1) * B + cb) * 4 * C + u0 + cu;
                 pre_v[0] = pr[0]; pre_v[1] = pr[C]; pre_v[2] = pr[2 * C]; pre_v[3] = pr[3 * C];
@@ -410,14 +414,14 @@ __global__ void __launch_bounds__(256) lstm_layer_kernel(const float* __restrict
 }
 
 int launch_lstm_layer(const float* pre, const float* Whh, float* hseq, float* hbuf, unsigned int* bar, int T, int B,
-                      int C, cudaStream_t s) {
+                      int C, cudaStream_t s, bf16* hseq_bf16) {
     SSRB_CHECK(C % LSTM_UPB == 0, "lstm: hidden size must be a multiple of 8");
     SSRB_CHECK(B <= 32, "lstm: batch chunk must be <= 32");
     const size_t smem = lstm_smem_bytes(C);
     SSRB_CUDA(cudaFuncSetAttribute(lstm_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SSRB_CUDA(cudaMemsetAsync(hbuf, 0, (size_t)2 * B * C * 4, s));
     SSRB_CUDA(cudaMemsetAsync(bar, 0, 4, s));
-    void* args[] = {(void*)&pre, (void*)&Whh, (void*)&hseq, (void*)&hbuf, (void*)&bar, (void*)&T, (void*)&B, (void*)&C};
+    void* args[] = {(void*)&pre, (void*)&Whh, (void*)&hseq, (void*)&hbuf, (void*)&bar, (void*)&T, (void*)&B, (void*)&C, (void*)&hseq_bf16};
     SSRB_CUDA(cudaLaunchCooperativeKernel((void*)lstm_layer_kernel, dim3(C / LSTM_UPB), dim3(256), args, smem, s));
     g_launch_count++;
     return 0;

@@ -12,12 +12,12 @@ int launch_conv1d(const float* in, int B, int Cin, int Tin, const float* W, cons
 int launch_convtr1d(const float* in, int B, int Cin, int Tin, const float* W, const float* bias, int Cout, int ksz,
                     int stride, int padL, int Tout, bool elu_in, float* out, cudaStream_t s);
 // [B,C,T] -> [T,B,C]
-int launch_bct_to_tbc(const float* in, int B, int C, int T, float* out, cudaStream_t s);
+int launch_bct_to_tbc(const float* in, int B, int C, int T, float* out, cudaStream_t s, bf16* out_bf16 = nullptr);
 // out[B,C,T] = seq[T,B,C] + skip[B,C,T]        (lstm.py:21-25)
 int launch_tbc_to_bct_add(const float* seq, const float* skip, int B, int C, int T, float* out, cudaStream_t s);
 // persistent recurrent pass of one LSTM layer (lstm.py:17 nn.LSTM): pre [T,B,4C] = x.Wih^T + b_ih + b_hh
 int launch_lstm_layer(const float* pre, const float* Whh, float* hseq, float* hbuf, unsigned int* bar, int T, int B,
-                      int C, cudaStream_t s);
+                      int C, cudaStream_t s, bf16* hseq_bf16 = nullptr);
 size_t lstm_smem_bytes(int C);
 // RVQ (core_vq.py:164-193,382-400).  emb [B,Dm,T] fp32; codebooks [n_q][bins][Dm]; cb_sq [n_q][bins]
 int launch_rvq_encode(const float* emb, int B, int Dm, int T, const float* codebooks, const float* cb_sq, int n_q,

@@ -28,5 +28,6 @@ int launch_cl_last_conv(const bf16* in_act, int B, int T, int C, const float* W 
                         float* wav, cudaStream_t s);
 int launch_cf32_to_cl(const float* in, int B, int C, int T, bool elu, bf16* out, cudaStream_t s);
 int launch_cl_to_cf32(const bf16* in, int B, int C, int T, float* out, cudaStream_t s);
+int launch_cl_zero_guards(bf16* p, int B, int T, int C, cudaStream_t s);
 
 }  // namespace ssrb
