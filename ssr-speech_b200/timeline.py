@@ -38,18 +38,20 @@ def capture(model, n_iters: int = 2, cap: int = 400000) -> np.ndarray:
 
 def launches(rec: np.ndarray):
     """Splits the records into kernel launches: same kernel id, dependency-resolved times within 3 us of each other."""
-    out = []
-    for kid in KERNELS:
-        r = rec[rec[:, 0] == kid]
-        if len(r) == 0:
-            continue
-        key = np.where(r[:, 3] > 0, r[:, 3], r[:, 2])
-        r = r[np.argsort(key, kind="stable")]
-        key = np.sort(key, kind="stable")
-        cuts = np.where(np.diff(key) > 3000)[0] + 1
-        for idxs in np.split(np.arange(len(r)), cuts):
-            out.append((kid, r[idxs]))
-    out.sort(key=lambda kr: float(np.where(kr[1][:, 3] > 0, kr[1][:, 3], kr[1][:, 2]).min()))
+    # A kernel's griddepcontrol.wait returns only after its predecessor has completely finished, so in dependency-resolved
+    # order the records of one launch are contiguous.  Split on kernel-id change; two back-to-back launches of the same
+    # kernel (FFN1 -> FFN2) are split where a record's dependency time is past every exit seen so far in the group.
+    key = np.where(rec[:, 3] > 0, rec[:, 3], rec[:, 2])
+    order = np.argsort(key, kind="stable")
+    rec, key = rec[order], key[order]
+    out, start, max_exit = [], 0, 0
+    for i in range(len(rec)):
+        if i > start and (rec[i, 0] != rec[start, 0] or (rec[i, 0] == 3 and max_exit > 0 and key[i] >= max_exit)):
+            out.append((int(rec[start, 0]), rec[start:i]))
+            start, max_exit = i, 0
+        max_exit = max(max_exit, int(rec[i, 4]))
+    if len(rec):
+        out.append((int(rec[start, 0]), rec[start:]))
     return out
 
 
