@@ -111,7 +111,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 template <int QROWS> struct TcCfg {
     static constexpr int Q_BYTES = QROWS * BK * 2;
     static constexpr int STAGE_BYTES = P_BYTES + Q_BYTES;
-    static constexpr int STAGES = QROWS >= 128 ? 3 : 4;
+    static constexpr int STAGES = 3;                                     // 3 x 24 KB: three swap-AB CTAs (or two flat ones) per SM
     static constexpr int TMEM_COLS = QROWS < 32 ? 32 : QROWS;
     static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
     static constexpr int PART_BYTES = QROWS * 128 * 4;                    // fp32 partial tile parked for the cluster reduce
@@ -120,7 +120,7 @@ template <int QROWS> struct TcCfg {
 };
 
 template <int QROWS, bool SWAP>
-__global__ void __launch_bounds__(192, 2) gemm_tc_kernel(const __grid_constant__ TmaGroup maps, const TcParams prm) {
+__global__ void __launch_bounds__(192, SWAP ? 3 : 2) gemm_tc_kernel(const __grid_constant__ TmaGroup maps, const TcParams prm) {
     using Cfg = TcCfg<QROWS>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B tiles need 1024 B alignment

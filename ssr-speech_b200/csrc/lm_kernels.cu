@@ -569,6 +569,7 @@ __global__ void __launch_bounds__(256) sample_kernel(const float* __restrict__ l
         }
         l[i] = a;
     }
+    ts_aux(ts, 0);
     // ---- top-k: threshold = k-th largest value (radix descent on order-preserving keys) -------------
     if (p.top_k > 0) {
         const int keff = min(max(p.top_k, 1), V);
@@ -592,6 +593,7 @@ __global__ void __launch_bounds__(256) sample_kernel(const float* __restrict__ l
 #pragma unroll
     for (int i = 0; i < SMP_NPT; i++) { e[i] = (l[i] == -INFINITY) ? 0.f : expf(l[i] - mx); zs += e[i]; }
     float Z = group_sum(zs, red, phase, k, wig, lane);
+    ts_aux(ts, 1);
     // ---- top-p: keep token i iff the probability mass ranked strictly above it is <= top_p ---------------
     if (p.top_p < 1.0f) {
         const float lim = p.top_p * Z;
@@ -611,6 +613,7 @@ __global__ void __launch_bounds__(256) sample_kernel(const float* __restrict__ l
         }
         Z = group_sum(zs, red, phase, k, wig, lane);
     }
+    ts_aux(ts, 2);
     // ---- sample: argmax_i (e_i / Z) / q_i, q ~ Exp(1); first index wins ties; also argmax of logits ----
     float bestv = -1.f; int besti = 0x7fffffff;
     float amv = -INFINITY; int ami = 0x7fffffff;
@@ -658,6 +661,7 @@ __global__ void __launch_bounds__(256) sample_kernel(const float* __restrict__ l
     }
     __syncthreads();
     if (threadIdx.x != 0) return;
+    ts_aux(ts, 3);
     // ---- state machine (single thread) ------------------------------------------------------------------
     UttState N = S;
     int smp[4] = {s_samples[0], s_samples[1], s_samples[2], s_samples[3]};

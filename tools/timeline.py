@@ -44,6 +44,11 @@ def main():
             med = lambda a: float(np.median(a)) / 1e3
             line += (f" | medians after dep: loads_issued={med(r[:, 5] - d):5.2f} accum={med(r[:, 6] - d):5.2f} parked={med(r[:, 7] - d):5.2f} "
                      f"cluster_bar={med(r[:, 8] - d):5.2f} reduced={med(r[:, 9] - d):5.2f} start={med(r[:, 2] - d):6.2f}")
+        if kid == 5:
+            d = dep.astype(np.float64)
+            med = lambda a: float(np.median(a)) / 1e3
+            line += (f" | medians after dep: loaded={med(r[:, 5] - d):5.2f} softmax={med(r[:, 6] - d):5.2f} top_p={med(r[:, 7] - d):5.2f} "
+                     f"sampled={med(r[:, 8] - d):5.2f} exit={med(r[:, 4] - d):5.2f}")
         print(line)
     print(timeline.critical_path(rec, args.iters))
 
