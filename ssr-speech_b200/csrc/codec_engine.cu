@@ -20,6 +20,7 @@ namespace {
 
 struct ConvW {
     float* w = nullptr; float* b = nullptr; int d0 = 0, d1 = 0, k = 0; bool has_w = false, has_b = false;
+    mutable float* wt = nullptr;        // [Cin][k][Cout] copy for conv1d_v2_kernel (built on first use)
     std::vector<float> hw, hb;          // host copies (folded weight, bias) for the tensor-core repack
 };
 // tensor-core operand of one convolution: W' [taps][N][Cw] bf16 (conv_tc.cu), fp32 bias (+ per-mark bias for wm_proj)
@@ -86,7 +87,7 @@ void ssrb_codec_destroy(ssrb_codec* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    for (auto& kv : c->convs) { cudaFree(kv.second.w); cudaFree(kv.second.b); }
+    for (auto& kv : c->convs) { cudaFree(kv.second.w); cudaFree(kv.second.b); cudaFree(kv.second.wt); }
     for (auto& kv : c->lstms) for (int l = 0; l < 4; l++) { cudaFree(kv.second.wih[l]); cudaFree(kv.second.whh[l]); cudaFree(kv.second.bsum[l]); }
     for (auto& kv : c->tcw) { cudaFree(kv.second.w); cudaFree(kv.second.bias); cudaFree(kv.second.bias_alt); }
     cudaFree(c->codebooks); cudaFree(c->cb_sq); cudaFree(c->wm_embed); cudaFree(c->bar); cudaFree(c->arena.base);
@@ -172,6 +173,7 @@ int ssrb_codec_load_tensor(ssrb_codec* c, const char* name_c, const float* host,
     if (leaf == "weight") {
         SSRB_CHECK(ndim == 3, "conv weight must be 3-D");
         W.d0 = (int)shape[0]; W.d1 = (int)shape[1]; W.k = (int)shape[2];
+        if (W.wt) { cudaFree(W.wt); W.wt = nullptr; }
         SSRB_TRY(upload_new(&W.w, host, n)); W.hw.assign(host, host + n); W.has_w = true; return 0;
     }
     if (leaf == "weight_g" || leaf == "weight_v") {
@@ -190,7 +192,8 @@ int ssrb_codec_load_tensor(ssrb_codec* c, const char* name_c, const float* host,
                 for (int64_t j = 0; j < inner; j++) w[i * inner + j] = P.v[i * inner + j] * sc;
             }
             W.d0 = (int)P.vshape[0]; W.d1 = (int)P.vshape[1]; W.k = (int)P.vshape[2];
-            SSRB_TRY(upload_new(&W.w, w.data(), w.size())); W.hw = w; W.has_w = true;
+            if (W.wt) { cudaFree(W.wt); W.wt = nullptr; }
+        SSRB_TRY(upload_new(&W.w, w.data(), w.size())); W.hw = w; W.has_w = true;
             c->pending.erase(prefix);
         }
         return 0;
@@ -217,7 +220,11 @@ static int conv(Ctx& x, const std::string& key, Tensor in, int stride, bool elu_
     const int Tout = (in.T + stride - 1) / stride;
     out->C = W->d0; out->T = Tout; out->p = x.c->arena.f((size_t)x.B * W->d0 * Tout);
     if (x.c->arena.dry) return 0;
-    return launch_conv1d(in.p, x.B, in.C, in.T, W->w, W->b, W->d0, k, stride, left, Tout, elu_in, res, out->p, x.s);
+    if (!W->wt) {
+        SSRB_TRY(dalloc((void**)&W->wt, (size_t)W->d0 * W->d1 * k * 4));
+        SSRB_TRY(launch_conv_w_transpose(W->w, W->wt, W->d0, W->d1, k, x.s));
+    }
+    return launch_conv1d(in.p, x.B, in.C, in.T, W->w, W->b, W->d0, k, stride, left, Tout, elu_in, res, out->p, x.s, W->wt);
 }
 // StreamableConvTranspose1d (conv.py:221-243); W [Cin][Cout][k]
 static int convtr(Ctx& x, const std::string& key, Tensor in, int stride, bool elu_in, Tensor* out) {
@@ -252,7 +259,7 @@ static int lstm(Ctx& x, const std::string& prefix, Tensor in, Tensor* out, bool 
     float* seq = A.f((size_t)T * B * C);
     float* pre = A.f((size_t)T * B * 4 * C);
     float* hs[2] = {A.f((size_t)T * B * C), A.f((size_t)T * B * C)};
-    float* hbuf = A.f((size_t)2 * B * C);
+    float* hbuf = A.f((size_t)2 * 32 * C);            // fp32 kernel: [2][B][C] fp32; tensor-core kernel: [2][32][C] bf16
     bf16* seq16 = tc ? (bf16*)A.f(((size_t)T * B * C + 1) / 2) : nullptr;
     bf16* hs16 = tc ? (bf16*)A.f(((size_t)T * B * C + 1) / 2) : nullptr;
     out->C = C; out->T = T; out->p = A.f((size_t)B * C * T);
@@ -276,7 +283,11 @@ static int lstm(Ctx& x, const std::string& prefix, Tensor in, Tensor* out, bool 
             g.A = cur; g.W = L.wih[l]; g.ab_dtype = SSRB_DTYPE_F32;
             SSRB_TRY(gemm_simt(g, x.s));
         }
-        SSRB_TRY(launch_lstm_layer(pre, L.whh[l], hs[l & 1], hbuf, x.c->bar, T, B, C, x.s, (tc && l + 1 < nl) ? hs16 : nullptr));
+        static const bool lstm_simt = [] { const char* e = getenv("SSRB_LSTM_SIMT"); return e && e[0] == '1'; }();
+        if (tc && lstm_mma_supported(C) && !lstm_simt)
+            SSRB_TRY(launch_lstm_layer_mma(pre, L.whh[l], hs[l & 1], (bf16*)hbuf, x.c->bar, T, B, C, x.s, l + 1 < nl ? hs16 : nullptr));
+        else
+            SSRB_TRY(launch_lstm_layer(pre, L.whh[l], hs[l & 1], hbuf, x.c->bar, T, B, C, x.s, (tc && l + 1 < nl) ? hs16 : nullptr));
         cur = hs[l & 1];
         cur16 = hs16;
     }

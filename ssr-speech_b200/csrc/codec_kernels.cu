@@ -95,6 +95,161 @@ __global__ void __launch_bounds__(256) conv1d_kernel(const float* __restrict__ i
     }
 }
 
+// =================================================================================================
+// Conv1d, register-tiled version for the layer shapes of the SEANet stacks (compile-time kernel size and stride).
+//   CTA tile = (16*TCO) output channels x 128 output steps, 256 threads; thread (ty, tx) owns TCO channels x
+//   two groups of 4 consecutive steps (tx*4 + {0,64}) -> every shared-memory access is a conflict-free LDS.128:
+//   one x window per (input channel, stride phase) serves all taps of that phase from registers, weights come
+//   pre-transposed as Wt[Cin][k][Cout].  Per-output accumulation order (ci outer, k inner) is the same as in
+//   conv1d_kernel above, so both kernels produce identical bits.
+// =================================================================================================
+template <int KSZ, int STRIDE, int TCO>
+__global__ void __launch_bounds__(256, 2) conv1d_v2_kernel(const float* __restrict__ in, int Cin, int Tin,
+                                                           const float* __restrict__ Wt, const float* __restrict__ bias,
+                                                           int Cout, int padL, int Tout, int elu_in,
+                                                           const float* __restrict__ res, float* __restrict__ out, int CI) {
+    constexpr int BCO = 16 * TCO, BT = 128;
+    constexpr int QO_MAX = (KSZ - 1) / STRIDE;            // largest tap shift inside one stride phase
+    constexpr int NW = (4 + QO_MAX + 3) / 4;              // float4 per x window
+    constexpr int QW = 124 + 4 * NW;                      // strip length per phase (covers the last window)
+    constexpr int STRIP = STRIDE * QW;
+    extern __shared__ __align__(16) float smem[];
+    float* in_s = smem;                                    // [CI][STRIDE][QW]
+    float* w_s = smem + CI * STRIP;                        // [CI][KSZ][BCO]
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int t0 = blockIdx.x * BT, c0 = blockIdx.y * BCO, b = blockIdx.z;
+    const float* inb = in + (int64_t)b * Cin * Tin;
+    const int gbase = t0 * STRIDE - padL;
+    float acc[TCO][8];
+#pragma unroll
+    for (int i = 0; i < TCO; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[i][j] = 0.f;
+    for (int ci0 = 0; ci0 < Cin; ci0 += CI) {
+        const int nci = min(CI, Cin - ci0);
+        __syncthreads();
+        for (int e = tid; e < nci * STRIP; e += 256) {
+            const int ci = e / STRIP, r = e - ci * STRIP;
+            const int g = gbase + r;
+            float v = 0.f;
+            if (g >= 0 && g < Tin) {
+                v = inb[(int64_t)(ci0 + ci) * Tin + g];
+                if (elu_in) v = elu1(v);
+            }
+            in_s[ci * STRIP + (r % STRIDE) * QW + r / STRIDE] = v;
+        }
+        {
+            const float* wsrc = Wt + (int64_t)ci0 * KSZ * Cout + c0;
+            constexpr int V = BCO / 4;                     // float4 per (ci,k) row
+            for (int e = tid; e < nci * KSZ * V; e += 256) {
+                const int r = e / V, c4 = (e - r * V) * 4;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c0 + c4 + 3 < Cout) v = *reinterpret_cast<const float4*>(wsrc + (int64_t)r * Cout + c4);
+                else {
+                    float t[4] = {0.f, 0.f, 0.f, 0.f};
+                    for (int z = 0; z < 4; z++) if (c0 + c4 + z < Cout) t[z] = wsrc[(int64_t)r * Cout + c4 + z];
+                    v = make_float4(t[0], t[1], t[2], t[3]);
+                }
+                *reinterpret_cast<float4*>(w_s + r * BCO + c4) = v;
+            }
+        }
+        __syncthreads();
+        for (int ci = 0; ci < nci; ci++) {
+#pragma unroll
+            for (int p = 0; p < STRIDE; p++) {
+                if (p >= KSZ) break;
+                float xw[2][4 * NW];
+#pragma unroll
+                for (int g = 0; g < 2; g++)
+#pragma unroll
+                    for (int n = 0; n < NW; n++) {
+                        const float4 t4 = *reinterpret_cast<const float4*>(in_s + ci * STRIP + p * QW + g * 64 + tx * 4 + 4 * n);
+                        xw[g][4 * n] = t4.x; xw[g][4 * n + 1] = t4.y; xw[g][4 * n + 2] = t4.z; xw[g][4 * n + 3] = t4.w;
+                    }
+#pragma unroll
+                for (int k = p; k < KSZ; k += STRIDE) {
+                    const int qo = k / STRIDE;
+                    float w[TCO];
+                    const float* wp = w_s + (ci * KSZ + k) * BCO + ty * TCO;
+                    if (TCO >= 4) {
+#pragma unroll
+                        for (int i = 0; i < TCO; i += 4) {
+                            const float4 t4 = *reinterpret_cast<const float4*>(wp + i);
+                            w[i] = t4.x; w[i + 1] = t4.y; w[i + 2] = t4.z; w[i + 3] = t4.w;
+                        }
+                    } else {
+                        const float2 t2 = *reinterpret_cast<const float2*>(wp);
+                        w[0] = t2.x; w[1] = t2.y;
+                    }
+#pragma unroll
+                    for (int i = 0; i < TCO; i++)
+#pragma unroll
+                        for (int g = 0; g < 2; g++)
+#pragma unroll
+                            for (int j = 0; j < 4; j++) acc[i][g * 4 + j] = fmaf(w[i], xw[g][j + qo], acc[i][g * 4 + j]);
+                }
+            }
+        }
+    }
+    const bool vec = (Tout & 3) == 0;
+#pragma unroll
+    for (int i = 0; i < TCO; i++) {
+        const int co = c0 + ty * TCO + i;
+        if (co >= Cout) continue;
+        const float bv = bias ? bias[co] : 0.f;
+#pragma unroll
+        for (int g = 0; g < 2; g++) {
+            const int t = t0 + g * 64 + tx * 4;
+            if (t >= Tout) continue;
+            const int64_t o = ((int64_t)b * Cout + co) * Tout + t;
+            if (vec) {                                      // Tout % 4 == 0 and t % 4 == 0: the float4 is in range and aligned
+                float4 v = make_float4(acc[i][g * 4] + bv, acc[i][g * 4 + 1] + bv, acc[i][g * 4 + 2] + bv, acc[i][g * 4 + 3] + bv);
+                if (res) { const float4 r4 = *reinterpret_cast<const float4*>(res + o); v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w; }
+                *reinterpret_cast<float4*>(out + o) = v;
+            } else {
+                for (int j = 0; j < 4 && t + j < Tout; j++) {
+                    float v = acc[i][g * 4 + j] + bv;
+                    if (res) v += res[o + j];
+                    out[o + j] = v;
+                }
+            }
+        }
+    }
+}
+
+__global__ void conv_w_transpose_kernel(const float* __restrict__ W, float* __restrict__ Wt, int Cout, int Cin, int ksz) {
+    const int64_t n = (int64_t)Cout * Cin * ksz;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        const int co = (int)(e % Cout);
+        const int64_t r = e / Cout;                        // r = ci*ksz + k
+        Wt[e] = W[(int64_t)co * Cin * ksz + r];
+    }
+}
+int launch_conv_w_transpose(const float* W, float* Wt, int Cout, int Cin, int ksz, cudaStream_t s) {
+    SSRB_LAUNCH(conv_w_transpose_kernel, 256, 256, 0, s, W, Wt, Cout, Cin, ksz);
+    return 0;
+}
+
+template <int KSZ, int STRIDE, int TCO>
+static int launch_conv1d_v2(const float* in, int B, int Cin, int Tin, const float* Wt, const float* bias, int Cout, int padL,
+                            int Tout, bool elu_in, const float* res, float* out, cudaStream_t s) {
+    constexpr int QO_MAX = (KSZ - 1) / STRIDE, NW = (4 + QO_MAX + 3) / 4, QW = 124 + 4 * NW, BCO = 16 * TCO;
+    constexpr int per_ci = STRIDE * QW + KSZ * BCO;
+    int CI = 24000 / per_ci;                               // ~96 KB per CTA -> two CTAs per SM
+    if (CI > 16) CI = 16;
+    if (CI > Cin) CI = Cin;
+    SSRB_CHECK(CI >= 1, "conv1d: kernel too large for the shared-memory tile");
+    const size_t smem = (size_t)CI * per_ci * 4;
+    static bool attr_done = false;
+    if (!attr_done) {
+        SSRB_CUDA(cudaFuncSetAttribute(conv1d_v2_kernel<KSZ, STRIDE, TCO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 24000 * 4));
+        attr_done = true;
+    }
+    dim3 grid(cdiv(Tout, 128), cdiv(Cout, BCO), B);
+    SSRB_LAUNCH((conv1d_v2_kernel<KSZ, STRIDE, TCO>), grid, 256, smem, s, in, Cin, Tin, Wt, bias, Cout, padL, Tout, (int)elu_in, res, out, CI);
+    return 0;
+}
+
 // single-output-channel conv (final decoder layer 64 -> 1, k7): memory bound, one thread per sample
 __global__ void __launch_bounds__(256) conv_cout1_kernel(const float* __restrict__ in, int Cin, int Tin,
                                                          const float* __restrict__ W, const float* __restrict__ bias,
@@ -122,13 +277,23 @@ __global__ void __launch_bounds__(256) conv_cout1_kernel(const float* __restrict
 }
 
 int launch_conv1d(const float* in, int B, int Cin, int Tin, const float* W, const float* bias, int Cout, int ksz,
-                  int stride, int padL, int Tout, bool elu_in, const float* res, float* out, cudaStream_t s) {
+                  int stride, int padL, int Tout, bool elu_in, const float* res, float* out, cudaStream_t s, const float* Wt) {
     if (Cout == 1 && stride == 1 && !res) {
         dim3 grid(cdiv(Tout, 256), B);
         SSRB_LAUNCH(conv_cout1_kernel, grid, 256, Cin * ksz * 4, s, in, Cin, Tin, W, bias, ksz, padL, Tout, (int)elu_in, out);
         return 0;
     }
     const int TCO = Cout >= 128 ? 8 : (Cout >= 64 ? 4 : 2);
+    static const bool v1 = [] { const char* e = getenv("SSRB_CONV_V1"); return e && e[0] == '1'; }();
+    if (Wt && !v1 && Cout % 4 == 0) {
+#define SSRB_CONV_V2(K, S, T)                                                                                           \
+    if (ksz == K && stride == S && TCO == T)                                                                            \
+        return launch_conv1d_v2<K, S, T>(in, B, Cin, Tin, Wt, bias, Cout, padL, Tout, elu_in, res, out, s);
+        SSRB_CONV_V2(7, 1, 4) SSRB_CONV_V2(7, 1, 8) SSRB_CONV_V2(3, 1, 2) SSRB_CONV_V2(3, 1, 4) SSRB_CONV_V2(3, 1, 8)
+        SSRB_CONV_V2(1, 1, 4) SSRB_CONV_V2(1, 1, 8) SSRB_CONV_V2(4, 2, 8) SSRB_CONV_V2(8, 4, 8) SSRB_CONV_V2(10, 5, 8)
+        SSRB_CONV_V2(16, 8, 8)
+#undef SSRB_CONV_V2
+    }
     const int BCO = 16 * TCO;
     const int Qw = 64 + (ksz - 1) / stride;
     const int per_ci = stride * Qw + ksz * BCO;
@@ -423,6 +588,139 @@ int launch_lstm_layer(const float* pre, const float* Whh, float* hseq, float* hb
     SSRB_CUDA(cudaMemsetAsync(bar, 0, 4, s));
     void* args[] = {(void*)&pre, (void*)&Whh, (void*)&hseq, (void*)&hbuf, (void*)&bar, (void*)&T, (void*)&B, (void*)&C, (void*)&hseq_bf16};
     SSRB_CUDA(cudaLaunchCooperativeKernel((void*)lstm_layer_kernel, dim3(C / LSTM_UPB), dim3(256), args, smem, s));
+    g_launch_count++;
+    return 0;
+}
+
+// =================================================================================================
+// LSTM recurrence on the tensor cores (bf16 decoder path only; the encoder keeps the fp32 kernel above because its
+// output decides RVQ indices).  Same decomposition — one cooperative CTA per 8 hidden units, one grid barrier per
+// step — but h_{t-1} . W_hh^T is D[32 gate rows x 32 batch] = W[32 x C] . h^T[C x 32] as bf16 mma.sync m16n8k16
+// with fp32 accumulation: warp w owns the k-slice [w*C/8, (w+1)*C/8); its W fragments are loaded ONCE and stay in
+// registers for all T steps, its h fragments are read straight from L2 (16-byte loads; the k order inside a slice
+// is permuted identically for both operands so that four lanes read 64 contiguous bytes), the 8 partial tiles meet in
+// shared memory.  Cell state and gate math stay fp32.
+// =================================================================================================
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int KS16>   // k-steps of 16 per warp: C = 8 warps x KS16 x 16
+__global__ void __launch_bounds__(256, 1) lstm_layer_mma_kernel(const float* __restrict__ pre, const float* __restrict__ Whh,
+                                                                float* __restrict__ hseq, bf16* hbuf /*[2][32][C]*/,
+                                                                unsigned int* bar, int T, int B, int C,
+                                                                bf16* __restrict__ hseq_bf16) {
+    __shared__ float red[8][4][32][LSTM_UPB];          // [warp][gate][batch][unit] partial pre-activations
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
+    const int u0 = blockIdx.x * LSTM_UPB;
+    const unsigned int G = gridDim.x;
+    const int kbase = warp * KS16 * 16;
+    // W fragments: tile row r = gate*8 + unit  <->  W_hh row gate*C + u0 + unit
+    uint32_t afr[2][KS16][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+        for (int ks = 0; ks < KS16; ks++) {
+            const int kp = kbase + (ks >> 1) * 32 + q * 8 + (ks & 1) * 4;
+            const float* plo = Whh + ((size_t)(2 * mt) * C + u0 + g) * C + kp;        // row mt*16 + g     : gate 2mt,   unit g
+            const float* phi = Whh + ((size_t)(2 * mt + 1) * C + u0 + g) * C + kp;    // row mt*16 + g + 8 : gate 2mt+1, unit g
+            afr[mt][ks][0] = pack_bf16x2(plo[0], plo[1]);
+            afr[mt][ks][1] = pack_bf16x2(phi[0], phi[1]);
+            afr[mt][ks][2] = pack_bf16x2(plo[2], plo[3]);
+            afr[mt][ks][3] = pack_bf16x2(phi[2], phi[3]);
+        }
+    const int cu = tid % LSTM_UPB, cb = tid / LSTM_UPB;
+    float c_state = 0.f;
+    float pre_v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (cb < B) {
+        const float* pr = pre + (size_t)cb * 4 * C + u0 + cu;
+        pre_v[0] = pr[0]; pre_v[1] = pr[C]; pre_v[2] = pr[2 * C]; pre_v[3] = pr[3 * C];
+    }
+    for (int t = 0; t < T; t++) {
+        const bf16* hprev = hbuf + (size_t)(t & 1) * 32 * C;
+        bf16* hnext = hbuf + (size_t)((t + 1) & 1) * 32 * C;
+        uint4 bv[4][KS16 / 2];
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int i = 0; i < KS16 / 2; i++)
+                bv[j][i] = __ldcg(reinterpret_cast<const uint4*>(hprev + (size_t)(j * 8 + g) * C + kbase + i * 32 + q * 8));
+        float acc[2][4][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+#pragma unroll
+                for (int z = 0; z < 4; z++) acc[mt][j][z] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < KS16; ks++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint4 v = bv[j][ks >> 1];
+                const uint32_t b0 = (ks & 1) ? v.z : v.x, b1 = (ks & 1) ? v.w : v.y;
+#pragma unroll
+                for (int mt = 0; mt < 2; mt++) mma_bf16_16816(acc[mt][j], afr[mt][ks], b0, b1);
+            }
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int n0 = j * 8 + 2 * q;
+                red[warp][2 * mt][n0][g] = acc[mt][j][0];
+                red[warp][2 * mt][n0 + 1][g] = acc[mt][j][1];
+                red[warp][2 * mt + 1][n0][g] = acc[mt][j][2];
+                red[warp][2 * mt + 1][n0 + 1][g] = acc[mt][j][3];
+            }
+        __syncthreads();
+        if (cb < B) {
+            float gs[4];
+#pragma unroll
+            for (int gate = 0; gate < 4; gate++) {
+                float a = 0.f;
+#pragma unroll
+                for (int w = 0; w < 8; w++) a += red[w][gate][cb][cu];      // fixed order: deterministic
+                gs[gate] = a + pre_v[gate];
+            }
+            c_state = sigmoidf_(gs[1]) * c_state + sigmoidf_(gs[0]) * tanhf(gs[2]);
+            const float hv = sigmoidf_(gs[3]) * tanhf(c_state);
+            hnext[(size_t)cb * C + u0 + cu] = __float2bfloat16_rn(hv);
+            hseq[((size_t)t * B + cb) * C + u0 + cu] = hv;
+            if (hseq_bf16) hseq_bf16[((size_t)t * B + cb) * C + u0 + cu] = __float2bfloat16_rn(hv);
+            if (t + 1 < T) {
+                const float* pr = pre + ((size_t)(t + 1) * B + cb) * 4 * C + u0 + cu;
+                pre_v[0] = pr[0]; pre_v[1] = pr[C]; pre_v[2] = pr[2 * C]; pre_v[3] = pr[3 * C];
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned int target = G * (unsigned int)(t + 1);
+            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+            unsigned int v;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+            } while (v < target);
+        }
+        __syncthreads();
+    }
+}
+
+bool lstm_mma_supported(int C) { return C == 256 || C == 512 || C == 1024; }
+
+int launch_lstm_layer_mma(const float* pre, const float* Whh, float* hseq, bf16* hbuf, unsigned int* bar, int T, int B,
+                          int C, cudaStream_t s, bf16* hseq_bf16) {
+    SSRB_CHECK(lstm_mma_supported(C), "lstm (tensor-core): hidden size must be 256, 512 or 1024");
+    SSRB_CHECK(B <= 32, "lstm: batch chunk must be <= 32");
+    SSRB_CUDA(cudaMemsetAsync(hbuf, 0, (size_t)2 * 32 * C * 2, s));
+    SSRB_CUDA(cudaMemsetAsync(bar, 0, 4, s));
+    void* args[] = {(void*)&pre, (void*)&Whh, (void*)&hseq, (void*)&hbuf, (void*)&bar, (void*)&T, (void*)&B, (void*)&C, (void*)&hseq_bf16};
+    const void* fn = C == 1024 ? (const void*)lstm_layer_mma_kernel<8> : C == 512 ? (const void*)lstm_layer_mma_kernel<4> : (const void*)lstm_layer_mma_kernel<2>;
+    SSRB_CUDA(cudaLaunchCooperativeKernel(fn, dim3(C / LSTM_UPB), dim3(256), args, 0, s));
     g_launch_count++;
     return 0;
 }

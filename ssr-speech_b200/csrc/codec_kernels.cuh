@@ -7,7 +7,10 @@ namespace ssrb {
 // out[b,co,t] = bias[co] + sum_{ci,k} W[co,ci,k] * f(in[b,ci,t*s+k-padL]) (+ res[b,co,t]);  f = ELU if elu_in.
 // Zero padding outside [0,Tin) (audiocraft/modules/conv.py:185-201).  W layout [Cout][Cin][ksz].
 int launch_conv1d(const float* in, int B, int Cin, int Tin, const float* W, const float* bias, int Cout, int ksz,
-                  int stride, int padL, int Tout, bool elu_in, const float* res, float* out, cudaStream_t s);
+                  int stride, int padL, int Tout, bool elu_in, const float* res, float* out, cudaStream_t s,
+                  const float* Wt = nullptr);
+// Wt [Cin][ksz][Cout] <- W [Cout][Cin][ksz]: operand layout of the register-tiled kernel (conv1d_v2_kernel)
+int launch_conv_w_transpose(const float* W, float* Wt, int Cout, int Cin, int ksz, cudaStream_t s);
 // transposed conv with the reference's trim (conv.py:221-243).  W layout [Cin][Cout][ksz], ksz == 2*stride.
 int launch_convtr1d(const float* in, int B, int Cin, int Tin, const float* W, const float* bias, int Cout, int ksz,
                     int stride, int padL, int Tout, bool elu_in, float* out, cudaStream_t s);
@@ -19,6 +22,10 @@ int launch_tbc_to_bct_add(const float* seq, const float* skip, int B, int C, int
 int launch_lstm_layer(const float* pre, const float* Whh, float* hseq, float* hbuf, unsigned int* bar, int T, int B,
                       int C, cudaStream_t s, bf16* hseq_bf16 = nullptr);
 size_t lstm_smem_bytes(int C);
+// the same recurrence with bf16 W_hh / h on mma.sync (fp32 accumulate, fp32 cell state); hbuf = [2][32][C] bf16
+bool lstm_mma_supported(int C);
+int launch_lstm_layer_mma(const float* pre, const float* Whh, float* hseq, bf16* hbuf, unsigned int* bar, int T, int B,
+                          int C, cudaStream_t s, bf16* hseq_bf16 = nullptr);
 // RVQ (core_vq.py:164-193,382-400).  emb [B,Dm,T] fp32; codebooks [n_q][bins][Dm]; cb_sq [n_q][bins]
 int launch_rvq_encode(const float* emb, int B, int Dm, int T, const float* codebooks, const float* cb_sq, int n_q,
                       int bins, float* residual_ws, long long* codes, cudaStream_t s);

@@ -15,11 +15,13 @@
 //         and every CTA reduces an interleaved subset of rows by reading its peers' tiles through
 //         distributed shared memory (ld.shared::cluster) in a fixed order (deterministic), then applies
 //         bias / activation / residual and stores — no global workspace, no atomics.
-//   FLAT  (prefill, large M): activations are the 128-row operand, a 128-wide weight tile is the N operand.
+//   FLAT2 (prefill, large M): persistent CTAs, 128 x 256 tiles, double-buffered TMEM accumulators (gemm_flat_kernel).
+//   FLAT  (SSRB_FLAT_OLD=1 / unaligned outputs): one 128 x 128 tile per CTA, 2 CTAs per SM.
 //
 // warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue.
 #include <cuda.h>
 
+#include <algorithm>
 #include <mutex>
 
 #include "common.cuh"
@@ -111,7 +113,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 template <int QROWS> struct TcCfg {
     static constexpr int Q_BYTES = QROWS * BK * 2;
     static constexpr int STAGE_BYTES = P_BYTES + Q_BYTES;
-    static constexpr int STAGES = 3;                                     // 3 x 24 KB: three swap-AB CTAs (or two flat ones) per SM
+    static constexpr int STAGES = QROWS >= 128 ? 3 : 4;
     static constexpr int TMEM_COLS = QROWS < 32 ? 32 : QROWS;
     static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
     static constexpr int PART_BYTES = QROWS * 128 * 4;                    // fp32 partial tile parked for the cluster reduce
@@ -120,7 +122,7 @@ template <int QROWS> struct TcCfg {
 };
 
 template <int QROWS, bool SWAP>
-__global__ void __launch_bounds__(192, SWAP ? 3 : 2) gemm_tc_kernel(const __grid_constant__ TmaGroup maps, const TcParams prm) {
+__global__ void __launch_bounds__(192, 2) gemm_tc_kernel(const __grid_constant__ TmaGroup maps, const TcParams prm) {
     using Cfg = TcCfg<QROWS>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B tiles need 1024 B alignment
@@ -394,6 +396,185 @@ __global__ void __launch_bounds__(192, SWAP ? 3 : 2) gemm_tc_kernel(const __grid
     }
 }
 
+// =================================================================================================================
+// FLAT2 (prefill, M > 128): persistent CTAs (one per SM), 128 x 256 output tiles, 4-stage 48 KB TMA ring, and TWO
+// 256-column TMEM accumulators: the epilogue warps drain tile j (TMEM -> registers -> bias/act/residual -> global)
+// while the MMA thread already accumulates tile j+1 into the other buffer.  A 128x128 tile reads 32 KB of shared
+// memory per 128x128x64 MMA block (~125 B/clk: the shared-memory port, not the tensor pipe, is the limit);
+// 128x256 reads 48 KB per 2x the math.
+// =================================================================================================================
+constexpr int F_N = 256;
+constexpr int F_STAGES = 4;
+constexpr int F_STAGE_BYTES = P_BYTES + F_N * BK * 2;
+constexpr size_t F_SMEM = (size_t)F_STAGES * F_STAGE_BYTES + 1024 + 256;
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,"
+        "%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(192, 1) gemm_flat_kernel(const __grid_constant__ TmaGroup maps, const TcParams prm, int m_tiles, int n_tiles) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = base + F_STAGES * F_STAGE_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (F_STAGES + s); };
+    auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * F_STAGES + b); };
+    auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * F_STAGES + 2 + b); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * F_STAGES + 4);
+
+    pdl_launch_dependents();
+    const int ts = ts_begin(TSK_GEMM);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const CUtensorMap* mapP = &maps.g[0].p;   // activations [M, K], box 128 rows
+    const CUtensorMap* mapQ = &maps.g[0].q;   // weights     [N, K], box 256 rows
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < F_STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int b = 0; b < 2; b++) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    const int total = m_tiles * n_tiles, nkb = prm.nkb;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            pdl_wait();                                   // activations come from the preceding kernel
+            ts_dep(ts);
+            int it = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+                const int mt = t / n_tiles, nt = t - mt * n_tiles;
+                for (int kb = 0; kb < nkb; kb++, it++) {
+                    const int s = it % F_STAGES;
+                    const uint32_t ph = (it / F_STAGES) & 1;
+                    mbar_wait(empty_bar(s), ph ^ 1);
+                    mbar_expect_tx(full_bar(s), F_STAGE_BYTES);
+                    const uint32_t sp = base + s * F_STAGE_BYTES;
+                    tma_load_2d(sp, mapP, full_bar(s), kb * BK, mt * P_ROWS);
+                    tma_load_2d(sp + P_BYTES, mapQ, full_bar(s), kb * BK, nt * F_N);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(F_N >> 3) << 17) | ((uint32_t)(P_ROWS >> 4) << 24);
+            int it = 0, j = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x, j++) {
+                const int buf = j & 1;
+                mbar_wait(tempty_bar(buf), ((j >> 1) & 1) ^ 1);        // epilogue has drained this accumulator
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t acc = tmem_base + (uint32_t)(buf * F_N);
+                for (int kb = 0; kb < nkb; kb++, it++) {
+                    const int s = it % F_STAGES;
+                    const uint32_t ph = (it / F_STAGES) & 1;
+                    mbar_wait(full_bar(s), ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t sp = base + s * F_STAGE_BYTES;
+                    const uint64_t da = make_desc(sp), db = make_desc(sp + P_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; k++) umma_bf16(acc, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    umma_commit(empty_bar(s));
+                }
+                umma_commit(tfull_bar(buf));
+            }
+        }
+    } else {
+        pdl_wait();                                       // residual / output buffers belong to the kernel chain
+        const int lg = warp & 3;
+        const int nl = lg * 32 + lane;
+        int j = 0;
+        for (int t = blockIdx.x; t < total; t += gridDim.x, j++) {
+            const int mt = t / n_tiles, nt = t - mt * n_tiles;
+            const int buf = j & 1;
+            mbar_wait(tfull_bar(buf), (j >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * F_N);
+            const int m = mt * P_ROWS + nl;
+            const bool mok = m < prm.M;
+#pragma unroll 1
+            for (int c0 = 0; c0 < F_N; c0 += 32) {
+                const int n0 = nt * F_N + c0;
+                if (n0 >= prm.N) break;                    // warp-uniform
+                float v[32];
+                tmem_ld32(taddr + c0, v);
+                if (!mok) continue;
+                if (n0 + 32 <= prm.N) {
+                    if (prm.bias) {
+#pragma unroll
+                        for (int q = 0; q < 32; q += 4) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(prm.bias + n0 + q));
+                            v[q] += b4.x; v[q + 1] += b4.y; v[q + 2] += b4.z; v[q + 3] += b4.w;
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < 32; q++) v[q] = apply_act(v[q], prm.act);
+                    if (prm.residual) {
+                        const float* rp = prm.residual + (long long)m * prm.ldr + n0;
+#pragma unroll
+                        for (int q = 0; q < 32; q += 4) {
+                            const float4 r4 = *reinterpret_cast<const float4*>(rp + q);
+                            v[q] += r4.x; v[q + 1] += r4.y; v[q + 2] += r4.z; v[q + 3] += r4.w;
+                        }
+                    }
+                    if (prm.c_dtype == SSRB_DTYPE_F32) {
+                        float* cp = reinterpret_cast<float*>(prm.C) + (long long)m * prm.ldc + n0;
+#pragma unroll
+                        for (int q = 0; q < 32; q += 4) *reinterpret_cast<float4*>(cp + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+                    } else {
+                        bf16* cp = reinterpret_cast<bf16*>(prm.C) + (long long)m * prm.ldc + n0;
+#pragma unroll
+                        for (int q = 0; q < 32; q += 8) {
+                            float w8[8];
+#pragma unroll
+                            for (int z = 0; z < 8; z++) w8[z] = v[q + z];
+                            store8(cp + q, w8);
+                        }
+                    }
+                } else {
+                    for (int q = 0; q < 32 && n0 + q < prm.N; q++) {
+                        const int n = n0 + q;
+                        float x = apply_act(v[q] + (prm.bias ? prm.bias[n] : 0.f), prm.act);
+                        if (prm.residual) x += prm.residual[(long long)m * prm.ldr + n];
+                        const long long o = (long long)m * prm.ldc + n;
+                        if (prm.c_dtype == SSRB_DTYPE_F32) reinterpret_cast<float*>(prm.C)[o] = x;
+                        else reinterpret_cast<bf16*>(prm.C)[o] = __float2bfloat16_rn(x);
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(buf));   // 4 arrivals (one per epilogue warp) free the accumulator
+        }
+    }
+    __syncwarp();
+    __syncthreads();
+    ts_end(ts);
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
 // ---- host side ------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -492,6 +673,23 @@ int gemm_tc(const GemmArgs& g, void*, size_t, cudaStream_t s) {
         }
     }
     prm.splits = 1; prm.kb_per_split = prm.nkb;
+    static const bool flat_old = [] { const char* e = getenv("SSRB_FLAT_OLD"); return e && e[0] == '1'; }();
+    const bool vec_ok = g.N % 4 == 0 && g.ldc % 8 == 0 && (!g.residual || g.ldr % 4 == 0) &&
+                        ((uintptr_t)g.C & 15) == 0 && ((uintptr_t)g.bias & 15) == 0 && ((uintptr_t)g.residual & 15) == 0;
+    if (!flat_old && vec_ok) {
+        static int n_sm = 0;
+        if (n_sm == 0) { int dev = 0; SSRB_CUDA(cudaGetDevice(&dev)); SSRB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev)); }
+        static bool attr_done = false;
+        if (!attr_done) {
+            SSRB_CUDA(cudaFuncSetAttribute(gemm_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM));
+            attr_done = true;
+        }
+        SSRB_TRY(make_map(&maps.g[0].p, A, g.M, g.K, g.lda, P_ROWS));
+        SSRB_TRY(make_map(&maps.g[0].q, W, g.N, g.K, g.ldw, F_N));
+        const int m_tiles = cdiv(g.M, P_ROWS), n_tiles = cdiv(g.N, F_N);
+        const int ctas = std::min(m_tiles * n_tiles, n_sm);
+        return launch_pdl(gemm_flat_kernel, dim3(ctas), dim3(192), F_SMEM, s, 1, maps, prm, m_tiles, n_tiles);
+    }
     SSRB_TRY(make_map(&maps.g[0].p, A, g.M, g.K, g.lda, P_ROWS));
     SSRB_TRY(make_map(&maps.g[0].q, W, g.N, g.K, g.ldw, 128));
     dim3 grid(cdiv(g.N, 128), cdiv(g.M, P_ROWS), 1);

@@ -465,7 +465,7 @@ int launch_attn_prefill(const float* qkv, int D, int H, const void* kcache, cons
 // =================================================================================================
 // Sampling head: CFG mix (ssr.py:690-696), logit rules (:698-730), temperature / top-k / top-p
 // (:26-86), sample = argmax(p / Exp(1)) (what torch.multinomial(n=1) evaluates), EOG bookkeeping and the
-// per-span state machine (:709-754,646-660).  One CTA per utterance, 4 groups of 64 threads = 4 codebooks.
+// per-span state machine (:709-754,646-660).  One CTA per (utterance, codebook), a cluster of 4 CTAs per utterance.
 // No host synchronisation: all Python-side control flow of the reference loop lives in UttState.
 // =================================================================================================
 __device__ __forceinline__ uint32_t fkey(float f) {
@@ -486,155 +486,210 @@ __device__ __forceinline__ uint32_t philox_u32(unsigned long long seed, uint32_t
     return c0;
 }
 
-constexpr int SMP_NPT = 33;   // values per thread: 64 threads x 33 >= 2056 classes
+constexpr int SMP_T = 256;   // threads per CTA
+constexpr int SMP_NPT = 9;   // values per thread: 256 threads x 9 >= 2056 classes
+constexpr int SMP_W = SMP_T / 32;
 
-struct GroupRed {
-    float f[2][4][2];
-    int i[2][4][2];
+struct BlockRed {
+    float f[2][SMP_W][4];
+    int i[2][SMP_W][4];
 };
 
-__device__ __forceinline__ float group_sum(float v, GroupRed& g, int& phase, int k, int wig, int lane) {
-    v = warp_sum(v);
-    if (lane == 0) g.f[phase][k][wig] = v;
-    __syncthreads();
-    const float r = g.f[phase][k][0] + g.f[phase][k][1];
-    phase ^= 1;
-    return r;
-}
-__device__ __forceinline__ float group_max(float v, GroupRed& g, int& phase, int k, int wig, int lane) {
-    v = warp_max(v);
-    if (lane == 0) g.f[phase][k][wig] = v;
-    __syncthreads();
-    const float r = fmaxf(g.f[phase][k][0], g.f[phase][k][1]);
-    phase ^= 1;
-    return r;
-}
-__device__ __forceinline__ int group_isum(int v, GroupRed& g, int& phase, int k, int wig, int lane) {
+// block-wide sums of N independent values with ONE __syncthreads (double-buffered scratch, fixed summation order)
+template <int N> __device__ __forceinline__ void block_sum(float (&v)[N], BlockRed& g, int& phase, int warp, int lane) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) g.i[phase][k][wig] = v;
+    for (int n = 0; n < N; n++) v[n] = warp_sum(v[n]);
+    if (lane == 0) {
+#pragma unroll
+        for (int n = 0; n < N; n++) g.f[phase][warp][n] = v[n];
+    }
     __syncthreads();
-    const int r = g.i[phase][k][0] + g.i[phase][k][1];
+#pragma unroll
+    for (int n = 0; n < N; n++) {
+        float r = 0.f;
+#pragma unroll
+        for (int w = 0; w < SMP_W; w++) r += g.f[phase][w][n];
+        v[n] = r;
+    }
+    phase ^= 1;
+}
+template <int N> __device__ __forceinline__ void block_isum(int (&v)[N], BlockRed& g, int& phase, int warp, int lane) {
+#pragma unroll
+    for (int n = 0; n < N; n++) v[n] = __reduce_add_sync(0xffffffffu, v[n]);
+    if (lane == 0) {
+#pragma unroll
+        for (int n = 0; n < N; n++) g.i[phase][warp][n] = v[n];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int n = 0; n < N; n++) {
+        int r = 0;
+#pragma unroll
+        for (int w = 0; w < SMP_W; w++) r += g.i[phase][w][n];
+        v[n] = r;
+    }
+    phase ^= 1;
+}
+__device__ __forceinline__ float block_max(float v, BlockRed& g, int& phase, int warp, int lane) {
+    v = warp_max(v);
+    if (lane == 0) g.f[phase][warp][0] = v;
+    __syncthreads();
+    float r = g.f[phase][0][0];
+#pragma unroll
+    for (int w = 1; w < SMP_W; w++) r = fmaxf(r, g.f[phase][w][0]);
     phase ^= 1;
     return r;
 }
 
-__global__ void __launch_bounds__(256) sample_kernel(const float* __restrict__ logits, UttState* __restrict__ st,
-                                                     int* __restrict__ seq_len, int* __restrict__ next_tok,
-                                                     int* __restrict__ gen_tok, const float* __restrict__ noise,
-                                                     int* __restrict__ iter_counter, SampleParams p) {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void st_cluster_u32(uint32_t local_addr, uint32_t rank, int v) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_addr), "r"(rank));
+    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(ra), "r"(v) : "memory");
+}
+__device__ __forceinline__ void cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// grid (n_utt, 4), cluster (1, 4, 1): CTA y of a cluster samples codebook y of utterance x; the four samples meet in the
+// shared memory of cluster rank 0 (DSMEM stores), whose thread 0 runs the per-utterance state machine.
+__global__ void __launch_bounds__(SMP_T) sample_kernel(const float* __restrict__ logits, UttState* __restrict__ st,
+                                                       int* __restrict__ seq_len, int* __restrict__ next_tok,
+                                                       int* __restrict__ gen_tok, const float* __restrict__ noise,
+                                                       int* __restrict__ iter_counter, SampleParams p) {
     pdl_launch_dependents();
     const int ts = ts_begin(TSK_SAMPLE);
     pdl_wait();
     ts_dep(ts);
-    __shared__ GroupRed red;
+    __shared__ BlockRed red;
     __shared__ int s_samples[4];
     __shared__ int s_argmax0;
-    __shared__ float s_bestv[4][2];
-    __shared__ int s_besti[4][2];
-    const int u = blockIdx.x;
-    if (u == 0 && threadIdx.x == 0) atomicAdd(iter_counter, 1);
+    __shared__ float s_bestv[SMP_W], s_amv[SMP_W];
+    __shared__ int s_besti[SMP_W], s_ami[SMP_W];
+    const int u = blockIdx.x, k = blockIdx.y;
+    if (u == 0 && k == 0 && threadIdx.x == 0) atomicAdd(iter_counter, 1);
     const UttState S = st[u];
-    if (S.done) return;
+    if (S.done) return;                                    // uniform over the cluster
     const int K = p.K, V = p.V;
-    const int k = threadIdx.x >> 6, t = threadIdx.x & 63, wig = (threadIdx.x >> 5) & 1, lane = threadIdx.x & 31;
+    const int t = threadIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int phase = 0;
     const int row0 = u * p.rpu;
     const bool use_cfg = (p.rpu == 2) && (S.cfg_tag == p.cfg_stride);
     const float c1 = p.cfg_coef, c2 = (float)(1.0 - (double)p.cfg_coef);
     const float* l0 = logits + ((int64_t)row0 * K + k) * V;
-    const float* l1 = logits + ((int64_t)(row0 + 1) * K + k) * V;
+    const float* l1 = logits + ((int64_t)(row0 + (use_cfg ? 1 : 0)) * K + k) * V;
+    // all loads first (independent, clamped), then the rules
+    float l[SMP_NPT], lu[SMP_NPT];
+#pragma unroll
+    for (int i = 0; i < SMP_NPT; i++) {
+        const int v = min(t + SMP_T * i, V - 1);
+        l[i] = l0[v];
+        lu[i] = l1[v];
+    }
     bool prev_sil = false;
     for (int i = 0; i < p.n_silence; i++) prev_sil |= (S.prev_token == p.silence[i]);
     const bool rep_rule = (S.num_eog == 0) && (k == 0) && p.stop_repetition > 0 && prev_sil &&
                           S.consec_silence > p.stop_repetition;
     const float rep_f = (float)(S.consec_silence - (p.stop_repetition - 1));
-    float l[SMP_NPT];
 #pragma unroll
     for (int i = 0; i < SMP_NPT; i++) {
-        const int v = t + 64 * i;
-        float a = -INFINITY;
-        if (v < V) {
-            a = l0[v];
-            if (use_cfg) a = __fadd_rn(__fmul_rn(c1, a), __fmul_rn(c2, l1[v]));
-            if (v == p.eos || v == p.sos || (v >= p.mts && v < p.mts + p.max_n_spans)) a = -10000.f;
-            if (S.num_gen < K - 1 && k >= S.num_gen + 1 && v == p.empty_token) a = 10000.f;
-            if (S.num_eog > 0) {
-                if (k >= S.num_eog + 1 && (v == p.eog || v == p.empty_token)) a = -10000.f;
-            } else {
-                if (k >= 1 && v == p.eog) a = -10000.f;
-                if (rep_rule && v == S.prev_token) a = a < 0.f ? a * rep_f : a / rep_f;
-            }
-            if (p.temperature != 1.0f) a = a / p.temperature;
+        const int v = t + SMP_T * i;
+        float a = l[i];
+        if (use_cfg) a = __fadd_rn(__fmul_rn(c1, a), __fmul_rn(c2, lu[i]));
+        if (v == p.eos || v == p.sos || (v >= p.mts && v < p.mts + p.max_n_spans)) a = -10000.f;
+        if (S.num_gen < K - 1 && k >= S.num_gen + 1 && v == p.empty_token) a = 10000.f;
+        if (S.num_eog > 0) {
+            if (k >= S.num_eog + 1 && (v == p.eog || v == p.empty_token)) a = -10000.f;
+        } else {
+            if (k >= 1 && v == p.eog) a = -10000.f;
+            if (rep_rule && v == S.prev_token) a = a < 0.f ? a * rep_f : a / rep_f;
         }
-        l[i] = a;
+        if (p.temperature != 1.0f) a = a / p.temperature;
+        l[i] = (v < V) ? a : -INFINITY;
     }
     ts_aux(ts, 0);
-    // ---- top-k: threshold = k-th largest value (radix descent on order-preserving keys) -------------
+    uint32_t key[SMP_NPT];
+#pragma unroll
+    for (int i = 0; i < SMP_NPT; i++) key[i] = fkey(l[i]);
+    // ---- top-k: threshold = k-th largest value.  Radix descent on the order-preserving keys, two bits per round
+    // (three candidate thresholds counted at once; identical to a bit-by-bit descent) ---------------------------------
     if (p.top_k > 0) {
         const int keff = min(max(p.top_k, 1), V);
         uint32_t T = 0;
-        for (int bit = 31; bit >= 0; bit--) {
-            const uint32_t cand = T | (1u << bit);
-            int c = 0;
+        for (int bit = 30; bit >= 0; bit -= 2) {
+            const uint32_t c1k = T | (1u << bit), c2k = T | (2u << bit), c3k = T | (3u << bit);
+            int c[3] = {0, 0, 0};
 #pragma unroll
-            for (int i = 0; i < SMP_NPT; i++) c += (t + 64 * i < V) && (fkey(l[i]) >= cand);
-            if (group_isum(c, red, phase, k, wig, lane) >= keff) T = cand;
+            for (int i = 0; i < SMP_NPT; i++) {
+                const bool in = t + SMP_T * i < V;
+                c[0] += in && key[i] >= c1k; c[1] += in && key[i] >= c2k; c[2] += in && key[i] >= c3k;
+            }
+            block_isum(c, red, phase, warp, lane);
+            T = c[2] >= keff ? c3k : c[1] >= keff ? c2k : c[0] >= keff ? c1k : T;
         }
 #pragma unroll
-        for (int i = 0; i < SMP_NPT; i++) if (fkey(l[i]) < T) l[i] = -INFINITY;
+        for (int i = 0; i < SMP_NPT; i++) if (key[i] < T) { l[i] = -INFINITY; key[i] = fkey(-INFINITY); }
     }
     float mx = -INFINITY;
 #pragma unroll
     for (int i = 0; i < SMP_NPT; i++) mx = fmaxf(mx, l[i]);
-    mx = group_max(mx, red, phase, k, wig, lane);
+    mx = block_max(mx, red, phase, warp, lane);
     float e[SMP_NPT];
-    float zs = 0.f;
+    float zs[1] = {0.f};
 #pragma unroll
-    for (int i = 0; i < SMP_NPT; i++) { e[i] = (l[i] == -INFINITY) ? 0.f : expf(l[i] - mx); zs += e[i]; }
-    float Z = group_sum(zs, red, phase, k, wig, lane);
+    for (int i = 0; i < SMP_NPT; i++) { e[i] = (l[i] == -INFINITY) ? 0.f : expf(l[i] - mx); zs[0] += e[i]; }
+    block_sum(zs, red, phase, warp, lane);
+    float Z = zs[0];
     ts_aux(ts, 1);
     // ---- top-p: keep token i iff the probability mass ranked strictly above it is <= top_p ---------------
     if (p.top_p < 1.0f) {
         const float lim = p.top_p * Z;
         uint32_t T = 0;
-        for (int bit = 31; bit >= 0; bit--) {
-            const uint32_t cand = T | (1u << bit);
-            float ms = 0.f;
+        for (int bit = 30; bit >= 0; bit -= 2) {
+            const uint32_t c1k = T | (1u << bit), c2k = T | (2u << bit), c3k = T | (3u << bit);
+            float ms[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-            for (int i = 0; i < SMP_NPT; i++) ms += (fkey(l[i]) >= cand) ? e[i] : 0.f;
-            if (group_sum(ms, red, phase, k, wig, lane) > lim) T = cand;
+            for (int i = 0; i < SMP_NPT; i++) {
+                ms[0] += key[i] >= c1k ? e[i] : 0.f; ms[1] += key[i] >= c2k ? e[i] : 0.f; ms[2] += key[i] >= c3k ? e[i] : 0.f;
+            }
+            block_sum(ms, red, phase, warp, lane);
+            T = ms[2] > lim ? c3k : ms[1] > lim ? c2k : ms[0] > lim ? c1k : T;
         }
-        zs = 0.f;
+        zs[0] = 0.f;
 #pragma unroll
         for (int i = 0; i < SMP_NPT; i++) {
-            if (fkey(l[i]) < T) { l[i] = -INFINITY; e[i] = 0.f; }
-            zs += e[i];
+            if (key[i] < T) { l[i] = -INFINITY; e[i] = 0.f; }
+            zs[0] += e[i];
         }
-        Z = group_sum(zs, red, phase, k, wig, lane);
+        block_sum(zs, red, phase, warp, lane);
+        Z = zs[0];
     }
     ts_aux(ts, 2);
     // ---- sample: argmax_i (e_i / Z) / q_i, q ~ Exp(1); first index wins ties; also argmax of logits ----
     float bestv = -1.f; int besti = 0x7fffffff;
     float amv = -INFINITY; int ami = 0x7fffffff;
     const float* nz = noise ? noise + (((int64_t)S.n_tok * p.n_utt + u) * K + k) * V : nullptr;
+    float qn[SMP_NPT];
 #pragma unroll
     for (int i = 0; i < SMP_NPT; i++) {
-        const int v = t + 64 * i;
+        const int v = min(t + SMP_T * i, V - 1);
+        if (nz) qn[i] = nz[v];
+        else {
+            const uint32_t rb = philox_u32(p.seed, (uint32_t)v, (uint32_t)k, (uint32_t)S.n_tok, (uint32_t)u);
+            qn[i] = fmaxf(-logf(((float)rb + 0.5f) * 2.3283064365386963e-10f), 1e-30f);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < SMP_NPT; i++) {
+        const int v = t + SMP_T * i;
         if (v < V) {
-            float qn;
-            if (nz) qn = nz[v];
-            else {
-                const uint32_t rb = philox_u32(p.seed, (uint32_t)v, (uint32_t)k, (uint32_t)S.n_tok, (uint32_t)u);
-                qn = -logf(((float)rb + 0.5f) * 2.3283064365386963e-10f);
-                qn = fmaxf(qn, 1e-30f);
-            }
-            const float sc = (e[i] / Z) / qn;
+            const float sc = (e[i] / Z) / qn[i];
             if (sc > bestv) { bestv = sc; besti = v; }     // ascending v within a thread: first index kept
             if (l[i] > amv) { amv = l[i]; ami = v; }
         }
     }
-    // reduce (value desc, index asc) over the 64 threads of the group
+    // reduce (value desc, index asc) over the block
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const float ov = __shfl_xor_sync(0xffffffffu, bestv, o);
@@ -644,23 +699,20 @@ __global__ void __launch_bounds__(256) sample_kernel(const float* __restrict__ l
         const int ai = __shfl_xor_sync(0xffffffffu, ami, o);
         if (av > amv || (av == amv && ai < ami)) { amv = av; ami = ai; }
     }
-    __shared__ float s_amv[4][2];
-    __shared__ int s_ami[4][2];
-    if (lane == 0) { s_bestv[k][wig] = bestv; s_besti[k][wig] = besti; s_amv[k][wig] = amv; s_ami[k][wig] = ami; }
+    if (lane == 0) { s_bestv[warp] = bestv; s_besti[warp] = besti; s_amv[warp] = amv; s_ami[warp] = ami; }
     __syncthreads();
-    if (threadIdx.x < 4) {
-        const int kk = threadIdx.x;
-        float bv = s_bestv[kk][0]; int bi = s_besti[kk][0];
-        if (s_bestv[kk][1] > bv || (s_bestv[kk][1] == bv && s_besti[kk][1] < bi)) { bv = s_bestv[kk][1]; bi = s_besti[kk][1]; }
-        s_samples[kk] = bi;
-        if (kk == 0) {
-            float av = s_amv[0][0]; int ai = s_ami[0][0];
-            if (s_amv[0][1] > av || (s_amv[0][1] == av && s_ami[0][1] < ai)) { av = s_amv[0][1]; ai = s_ami[0][1]; }
-            s_argmax0 = ai;
+    if (threadIdx.x == 0) {
+        float bv = s_bestv[0]; int bi = s_besti[0];
+        float av = s_amv[0]; int ai = s_ami[0];
+        for (int w = 1; w < SMP_W; w++) {
+            if (s_bestv[w] > bv || (s_bestv[w] == bv && s_besti[w] < bi)) { bv = s_bestv[w]; bi = s_besti[w]; }
+            if (s_amv[w] > av || (s_amv[w] == av && s_ami[w] < ai)) { av = s_amv[w]; ai = s_ami[w]; }
         }
+        st_cluster_u32(smem_u32(&s_samples[k]), 0, bi);
+        if (k == 0) s_argmax0 = ai;
     }
-    __syncthreads();
-    if (threadIdx.x != 0) return;
+    cluster_barrier();                                     // the four samples are in rank 0's shared memory
+    if (k != 0 || threadIdx.x != 0) return;
     ts_aux(ts, 3);
     // ---- state machine (single thread) ------------------------------------------------------------------
     UttState N = S;
@@ -703,8 +755,9 @@ __global__ void __launch_bounds__(256) sample_kernel(const float* __restrict__ l
 int launch_sample(const float* logits, UttState* st, int* seq_len, int* next_tok, int* gen_tok, const float* noise,
                   int* iter_counter, const SampleParams& p, cudaStream_t s) {
     SSRB_CHECK(p.K == 4, "sample: n_codebooks must be 4");
-    SSRB_CHECK(p.V <= 64 * SMP_NPT, "sample: audio vocabulary too large for the sampling kernel");
-    SSRB_LAUNCH_PDL(sample_kernel, p.n_utt, 256, 0, s, logits, st, seq_len, next_tok, gen_tok, noise, iter_counter, p);
+    SSRB_CHECK(p.V <= SMP_T * SMP_NPT, "sample: audio vocabulary too large for the sampling kernel");
+    SSRB_TRY(launch_pdl(sample_kernel, dim3(p.n_utt, 4), dim3(SMP_T), 0, s, /*cluster_y=*/4, logits, st, seq_len, next_tok, gen_tok,
+                        noise, iter_counter, p));
     return 0;
 }
 

@@ -67,7 +67,7 @@ def test_simt_bf16(M, N, K):
 
 TC_SHAPES = [(1, 768, 256), (2, 6144, 2048), (16, 2048, 2048), (17, 2056, 1024), (64, 6144, 2048), (64, 2048, 8192),
              (64, 8192, 2048), (100, 4096, 2048), (128, 2048, 2048), (129, 2048, 2048), (611, 6144, 2048), (1000, 2056, 1024),
-             (300, 8192, 2048)]
+             (300, 8192, 2048), (20000, 1024, 512), (5000, 4096, 2048), (4097, 264, 128)]
 
 
 @pytest.mark.parametrize("M,N,K", TC_SHAPES)
