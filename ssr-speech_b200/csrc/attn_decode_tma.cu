@@ -63,16 +63,21 @@ __device__ __forceinline__ void lds8_bf16(uint32_t addr, float (&v)[8]) {
 __global__ void __launch_bounds__(160, 2) attn_decode_tma_kernel(const float* __restrict__ qkv, int D, int H, bf16* kc, bf16* vc,
                                                                  int Smax, const int* __restrict__ seq_len,
                                                                  const UttState* __restrict__ st, int rpu, float* ws,
-                                                                 int* __restrict__ tickets, bf16* __restrict__ out) {
+                                                                 int* __restrict__ tickets, bf16* __restrict__ out, int prefetch) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ float sm_m[8], sm_l[8], sm_o[8][128];
     __shared__ int sm_last;
     pdl_launch_dependents();
     const int ts = ts_begin(TSK_ATTN);
-    pdl_wait();        // everything this kernel reads (state, cache rows of earlier steps, q/k/v) is produced upstream
-    ts_dep(ts);
+    // prefetch == 0: wait for the predecessor before reading anything.  prefetch == 1 (decode chain): the row state (done,
+    // seq_len) was written by the previous iteration's sampler and the cached K/V rows [0, n_old) by earlier iterations; the
+    // embed kernel that opens every iteration releases its dependents only AFTER its own griddepcontrol.wait, so no kernel
+    // of this iteration — this one included — can start before the previous iteration has completed and flushed.  Only q
+    // and this step's K/V row come from the QKV GEMM right before: the consumers wait for it, the producer warp starts
+    // streaming the cache at once, so the K/V stream overlaps the tail of the GEMM.
+    if (!prefetch) { pdl_wait(); ts_dep(ts); }
     const int h = blockIdx.x, r = blockIdx.y, z = blockIdx.z, nz = gridDim.z;
-    if (st[r / rpu].done) return;
+    if (st[r / rpu].done) { if (prefetch) pdl_wait(); return; }     // every CTA waits: completion stays transitive along the chain
     const int n_keys = seq_len[r] + 1;
     const int n_old = n_keys - 1;                                         // keys already in the cache
     const int tiles_total = (n_old + AT_SUB - 1) / AT_SUB;               // sub-tiles of cached keys
@@ -80,7 +85,7 @@ __global__ void __launch_bounds__(160, 2) attn_decode_tma_kernel(const float* __
     // also owns the new key.  CTAs with no work exit (nsplit_eff counts the ones that take a ticket).
     const int per = (tiles_total + nz - 1) / nz;
     const int nsplit_eff = per > 0 ? (tiles_total + per - 1) / per : 1;   // >= 1 (a row with no cached key: 1 CTA)
-    if (z >= nsplit_eff) return;
+    if (z >= nsplit_eff) { if (prefetch) pdl_wait(); return; }
     const int t0 = z * per, t1 = min(tiles_total, t0 + per);
     const int my_tiles = t1 - t0;
     const bool has_new = (z == nsplit_eff - 1);
@@ -113,6 +118,7 @@ __global__ void __launch_bounds__(160, 2) attn_decode_tma_kernel(const float* __
     }
 
     // ===== consumers (warps 0-3) =====
+    if (prefetch) { pdl_wait(); ts_dep(ts); }
     const float scale = 0.08838834764831845f;          // 1/sqrt(128)
     float q[8];
     load8(qkv + (int64_t)r * 3 * D + h * 128 + dl, q);
@@ -249,7 +255,7 @@ int attn_decode_tma_nsplit(int R, int H, int Smax) {
 int attn_decode_tma_max_nsplit(int Smax) { return cdiv(Smax, 2 * AT_SUB); }
 
 int launch_attn_decode_tma(const float* qkv, int R, int D, int H, void* kcache, void* vcache, int Smax, const int* seq_len,
-                           const UttState* st, int rpu, float* ws, int* tickets, void* out, cudaStream_t s) {
+                           const UttState* st, int rpu, float* ws, int* tickets, void* out, int prefetch, cudaStream_t s) {
     static bool attr_done = false;
     if (!attr_done) {
         SSRB_CUDA(cudaFuncSetAttribute(attn_decode_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
@@ -257,7 +263,7 @@ int launch_attn_decode_tma(const float* qkv, int R, int D, int H, void* kcache, 
     }
     dim3 grid(H, R, attn_decode_tma_nsplit(R, H, Smax));
     return launch_pdl(attn_decode_tma_kernel, grid, dim3(160), AT_SMEM, s, 1, qkv, D, H, (bf16*)kcache, (bf16*)vcache, Smax, seq_len,
-                      st, rpu, ws, tickets, (bf16*)out);
+                      st, rpu, ws, tickets, (bf16*)out, prefetch);
 }
 
 int ts_arm_attn_tma(const TsBuf& t) { return ts_arm_tu(t); }

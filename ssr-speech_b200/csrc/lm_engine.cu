@@ -23,6 +23,12 @@ bool pdl_enabled() {
     return on;
 }
 
+// SSRB_ATTN_PREFETCH=0: the decode attention waits for the QKV GEMM before it starts streaming the cache
+static bool attn_prefetch_enabled() {
+    static const bool on = [] { const char* e = getenv("SSRB_ATTN_PREFETCH"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
 template <typename T>
 __global__ void convert_kernel(const float* __restrict__ src, T* __restrict__ dst, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -301,7 +307,7 @@ static int run_layer(ssrb_lm* lm, int n, int M, bool prefill, int n_rows, int ma
     } else {
         ProfScope ps(lm, PC_ATTN, s);   // the decode attention kernel also appends this step's K/V row in place
         SSRB_TRY(launch_attn_decode(lm->qkv, M, D, H, kc, vc, lm->wdt, lm->cfg.max_seq, lm->d_seq_len, lm->d_state,
-                                    lm->rpu, lm->attn_ws, lm->tickets, lm->ao, lm->wdt, s));
+                                    lm->rpu, lm->attn_ws, lm->tickets, lm->ao, lm->wdt, attn_prefetch_enabled() ? 1 : 0, s));
     }
     g = GemmArgs();
     g.A = lm->ao; g.lda = D; g.W = w.wo; g.ldw = D; g.bias = w.bo; g.residual = lm->x; g.ldr = D; g.C = lm->x; g.ldc = D;

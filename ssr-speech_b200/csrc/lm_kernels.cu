@@ -40,9 +40,11 @@ __global__ void __launch_bounds__(256) embed_prefill_kernel(const PosDesc* __res
 __global__ void __launch_bounds__(256) embed_step_kernel(const int* __restrict__ next_tok, const UttState* __restrict__ st,
                                                          int rpu, int K, int D, const float* __restrict__ audio_emb, int V,
                                                          const float* __restrict__ pe, float alpha_a, float* __restrict__ x) {
-    pdl_launch_dependents();
     const int ts = ts_begin(TSK_EMBED);
     pdl_wait();
+    // first kernel of a decode iteration: dependents are released only once the previous iteration (sampler included) has
+    // completed, so kernels further down the chain may read the row state / cached K/V before their own griddepcontrol.wait
+    pdl_launch_dependents();
     ts_dep(ts);
     const int r = blockIdx.x, u = r / rpu;
     const int* tk = next_tok + u * K;
@@ -316,7 +318,7 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const float* __restric
 
 int launch_attn_decode(const float* qkv, int R, int D, int H, const void* kcache, const void* vcache, int cache_dtype,
                        int Smax, const int* seq_len, const UttState* st, int rpu, float* ws, int* tickets,
-                       void* out, int out_dtype, cudaStream_t s) {
+                       void* out, int out_dtype, int prefetch, cudaStream_t s) {
     dim3 grid(H, R, attn_decode_nsplit(Smax));
     if (cache_dtype == SSRB_DTYPE_F32) {
         SSRB_CHECK(out_dtype == SSRB_DTYPE_F32, "attn_decode: fp32 cache implies fp32 activations");
@@ -327,7 +329,7 @@ int launch_attn_decode(const float* qkv, int R, int D, int H, const void* kcache
         static const bool simple = [] { const char* e = getenv("SSRB_ATTN_SIMPLE"); return e && e[0] == '1'; }();
         if (!simple)
             return launch_attn_decode_tma(qkv, R, D, H, const_cast<void*>(kcache), const_cast<void*>(vcache), Smax, seq_len, st,
-                                          rpu, ws, tickets, out, s);
+                                          rpu, ws, tickets, out, prefetch, s);
         SSRB_LAUNCH_PDL((attn_decode_kernel<bf16, bf16>), grid, 128, 0, s, qkv, D, H, (const bf16*)kcache,
                     (const bf16*)vcache, Smax, seq_len, st, rpu, ws, tickets, (bf16*)out);
     }

@@ -56,7 +56,8 @@ def base():
     return run({})
 
 
-@pytest.mark.parametrize("env", [{"SSRB_NO_PDL": "1"}, {"SSRB_NO_GRAPH": "1"}, {"SSRB_NO_PDL": "1", "SSRB_NO_GRAPH": "1"}])
+@pytest.mark.parametrize("env", [{"SSRB_NO_PDL": "1"}, {"SSRB_NO_GRAPH": "1"}, {"SSRB_NO_PDL": "1", "SSRB_NO_GRAPH": "1"},
+                                 {"SSRB_ATTN_PREFETCH": "0"}])   # K/V stream started before / after griddepcontrol.wait
 def test_scheduling_modes_are_bit_identical(base, env):
     other = run(env)
     assert other["n_frames"] == base["n_frames"]

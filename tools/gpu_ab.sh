@@ -1,0 +1,21 @@
+#!/bin/bash
+# A/B of scheduling switches on the bench workload (no CPU baseline), after the GEMM / mode tests.
+set -u
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_gemm.py tests/test_gpu_modes.py tests/test_gpu_lm.py -m gpu -x -q > gpurun_out/pytest_ab.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_ab.log
+tail -4 gpurun_out/pytest_ab.log
+run() { name=$1; shift; env "$@" timeout 400 python bench.py --no-cpu-baseline --steps 2 --warmup 3 > gpurun_out/ab_$name.json 2> gpurun_out/ab_$name.err; echo "$name rc=$?"; python - <<PY
+import json
+try:
+    d=json.loads(open("gpurun_out/ab_$name.json").read().strip().splitlines()[-1])
+    b=d["roofline"]["breakdown"]
+    print("$name", "value", round(d["value"]), "e2e", round(d["e2e"]["value"]), "frac", round(d["roofline"]["frac"],4), "iter_ms", round(d["roofline"]["iteration_ms_avg"],4),
+          "attn", round(b["attention_us"]), "gemm", round(b["gemm_us"]), "ln", round(b["layernorm_us"]), "phases", {k:round(v,1) for k,v in d["e2e"]["phase_ms_per_step"].items()})
+except Exception as e:
+    print("$name failed", e)
+PY
+}
+for spec in "$@"; do
+  name=${spec%%:*}; envs=${spec#*:}
+  run $name ${envs//,/ }
+done
