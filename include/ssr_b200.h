@@ -111,6 +111,19 @@ int ssrb_lm_decode(ssrb_lm* lm, int n_steps, void* stream);
  * loop iterations executed so far (1 = only the prefill sample). */
 int ssrb_lm_poll(ssrb_lm* lm, void* stream, int* n_done, int* n_iter);
 
+/* Continuous batching (the reference decodes one utterance at a time, inference_v2.py:331-333): replaces the
+ * FINISHED utterance in slot `utt` of the open batch by a new one — prologue + first dec_forward + first sample of
+ * SSR_Speech.inference (ssr.py:596-689) for that utterance only, into the slot's KV rows; the other slots keep decoding
+ * from where they are.  text [rows_per_utt, text_len] (cond row, then the uncond row when aug_text), prompt
+ * [n_codebooks, prompt_len] as in ssrb_lm_batch.  `rng_stream` selects the utterance's Philox stream (its index in a plain
+ * batch), so its samples do not depend on the slot or the moment it was admitted.  Capacity (max_seq, max_steps,
+ * max_prefill_tokens) is that of the engine; batches begun with injected noise cannot admit.  Synchronises once (reads
+ * the slot state), the prefill itself is asynchronous. */
+int ssrb_lm_admit(ssrb_lm* lm, int utt, const int32_t* text, int text_len, const int32_t* prompt, int prompt_len,
+                  int n_spans, int rng_stream, void* stream);
+/* Like ssrb_lm_poll, per slot: done_flags[n_utt] (1 = all spans finished).  Synchronises. */
+int ssrb_lm_poll_flags(ssrb_lm* lm, void* stream, int32_t* done_flags, int* n_iter);
+
 /* Sampled tokens of utterance `utt`: out[n, n_codebooks] int32 for n = 0..*n_tokens-1 (every iteration
  * of every span, including each span's EOG tail, concatenated); span_len[max_n_spans] = iterations per
  * span.  Capacity `cap` iterations.  Synchronises. */

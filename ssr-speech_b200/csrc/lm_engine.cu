@@ -353,6 +353,8 @@ static int enqueue_step(ssrb_lm* lm, cudaStream_t s) {
     return 0;
 }
 
+static int heads_on_rows(ssrb_lm* lm, int r0, int M, cudaStream_t s);
+
 // ---- prefill ----------------------------------------------------------------------------------------
 struct RowPlan { int r, u, lx, plen, len; };
 
@@ -430,7 +432,7 @@ int ssrb_lm_begin(ssrb_lm* lm, const ssrb_lm_batch* b, const ssrb_sampling* sp, 
         SSRB_CHECK(b->n_spans[u] >= 1 && b->n_spans[u] <= lm->cfg.max_n_spans, "n_spans out of range");
         SSRB_CHECK(lx + pl + 1 + lm->cfg.max_steps <= lm->cfg.max_seq, "max_seq too small for text + prompt + max_steps");
         SSRB_CHECK(pl + 1 + lm->cfg.max_steps <= lm->n_pos && lx <= lm->n_pos, "PE table too small");
-        UttState z{}; z.cfg_tag = 1; z.prev_token = -1; z.n_spans = b->n_spans[u]; z.x_len = lx; z.y_len = pl;
+        UttState z{}; z.cfg_tag = 1; z.prev_token = -1; z.n_spans = b->n_spans[u]; z.x_len = lx; z.y_len = pl; z.rng_id = u;
         st[u] = z;
         for (int j = 0; j < rpu; j++) { seq[u * rpu + j] = lx + pl; plan.push_back({u * rpu + j, u, lx, pl, lx + pl + 1}); }
     }
@@ -447,18 +449,83 @@ int ssrb_lm_begin(ssrb_lm* lm, const ssrb_lm_batch* b, const ssrb_sampling* sp, 
     }
     if (!chunk.empty()) SSRB_TRY(prefill_chunk(lm, chunk, b, s, nullptr));
     // heads on every row's last position, then iteration 1's sample
-    const int D = lm->D, V = lm->V, Hh = lm->Hh;
-    GemmArgs g;
-    g.A = lm->hlast; g.lda = D; g.W = lm->hw1; g.ldw = D; g.bias = lm->hb1; g.C = lm->hh; g.ldc = K * Hh;
-    g.M = R; g.N = K * Hh; g.K = D; g.act = ACT_GELU; g.c_dtype = lm->wdt;
-    SSRB_TRY(gemm(lm, g, s));
-    g = GemmArgs();
-    g.A = lm->hh; g.lda = K * Hh; g.a_gs = Hh; g.W = lm->hw2; g.ldw = Hh; g.w_gs = (int64_t)V * Hh;
-    g.bias = lm->hb2; g.bias_gs = V; g.C = lm->logits; g.ldc = (int64_t)K * V; g.c_gs = V;
-    g.M = R; g.N = V; g.K = Hh; g.groups = K; g.c_dtype = SSRB_DTYPE_F32;
-    SSRB_TRY(gemm(lm, g, s));
+    SSRB_TRY(heads_on_rows(lm, 0, R, s));
     SSRB_TRY(launch_sample(lm->logits, lm->d_state, lm->d_seq_len, lm->d_next_tok, lm->d_gen_tok, lm->noise, lm->d_iter,
                            lm->sp, s));
+    return 0;
+}
+
+// heads on rows [r0, r0 + M) of hlast -> logits rows [r0, r0 + M)
+static int heads_on_rows(ssrb_lm* lm, int r0, int M, cudaStream_t s) {
+    const int D = lm->D, V = lm->V, Hh = lm->Hh, K = lm->K;
+    const size_t e = lm->esz;
+    GemmArgs g;
+    g.A = (char*)lm->hlast + (size_t)r0 * D * e; g.lda = D; g.W = lm->hw1; g.ldw = D; g.bias = lm->hb1;
+    g.C = (char*)lm->hh + (size_t)r0 * K * Hh * e; g.ldc = K * Hh;
+    g.M = M; g.N = K * Hh; g.K = D; g.act = ACT_GELU; g.c_dtype = lm->wdt;
+    SSRB_TRY(gemm(lm, g, s));
+    g = GemmArgs();
+    g.A = (char*)lm->hh + (size_t)r0 * K * Hh * e; g.lda = K * Hh; g.a_gs = Hh; g.W = lm->hw2; g.ldw = Hh; g.w_gs = (int64_t)V * Hh;
+    g.bias = lm->hb2; g.bias_gs = V; g.C = lm->logits + (size_t)r0 * K * V; g.ldc = (int64_t)K * V; g.c_gs = V;
+    g.M = M; g.N = V; g.K = Hh; g.groups = K; g.c_dtype = SSRB_DTYPE_F32;
+    SSRB_TRY(gemm(lm, g, s));
+    return 0;
+}
+
+int ssrb_lm_admit(ssrb_lm* lm, int utt, const int32_t* text, int text_len, const int32_t* prompt, int prompt_len,
+                  int n_spans, int rng_stream, void* stream) {
+    SSRB_CHECK(lm && lm->R > 0 && text && (prompt || prompt_len == 0), "no open batch / null argument");
+    SSRB_CHECK(utt >= 0 && utt < lm->n_utt, "bad utterance slot");
+    SSRB_CHECK(lm->noise == nullptr, "a batch with injected sampling noise cannot admit utterances");
+    SSRB_CUDA(cudaSetDevice(lm->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const int rpu = lm->rpu, K = lm->K, r0 = utt * rpu;
+    SSRB_CHECK(text_len > 0 && prompt_len >= 0, "bad text/prompt length");
+    SSRB_CHECK(n_spans >= 1 && n_spans <= lm->cfg.max_n_spans, "n_spans out of range");
+    SSRB_CHECK(text_len + prompt_len + 1 + lm->cfg.max_steps <= lm->cfg.max_seq, "max_seq too small for text + prompt + max_steps");
+    SSRB_CHECK(prompt_len + 1 + lm->cfg.max_steps <= lm->n_pos && text_len <= lm->n_pos, "PE table too small");
+    SSRB_CHECK(text_len + prompt_len + 1 <= lm->cfg.max_prefill_tokens, "one prompt exceeds max_prefill_tokens");
+    // the slot must have finished: its rows are about to be overwritten
+    UttState cur;
+    SSRB_CUDA(cudaMemcpyAsync(&cur, lm->d_state + utt, sizeof(UttState), cudaMemcpyDeviceToHost, s));
+    SSRB_CUDA(cudaStreamSynchronize(s));
+    SSRB_CHECK(cur.done, "slot still decoding");
+    // host view addressed by absolute row / utterance index, as prefill_chunk expects
+    const int ps = prompt_len > 0 ? prompt_len : 1;
+    std::vector<int32_t> text_full((size_t)lm->R * text_len, 0), prompt_full((size_t)lm->n_utt * K * ps, 0);
+    for (int j = 0; j < rpu; j++)
+        std::copy(text + (size_t)j * text_len, text + (size_t)(j + 1) * text_len, text_full.begin() + (size_t)(r0 + j) * text_len);
+    for (int k = 0; k < K; k++)
+        std::copy(prompt + (size_t)k * prompt_len, prompt + (size_t)(k + 1) * prompt_len, prompt_full.begin() + ((size_t)utt * K + k) * ps);
+    ssrb_lm_batch b{};
+    b.n_utt = lm->n_utt; b.text = text_full.data(); b.text_stride = text_len; b.prompt = prompt_full.data(); b.prompt_stride = ps;
+    UttState z{}; z.cfg_tag = 1; z.prev_token = -1; z.n_spans = n_spans; z.x_len = text_len; z.y_len = prompt_len; z.rng_id = rng_stream;
+    std::vector<int> seq(rpu, text_len + prompt_len);
+    SSRB_CUDA(cudaMemcpyAsync(lm->d_state + utt, &z, sizeof(UttState), cudaMemcpyHostToDevice, s));
+    SSRB_CUDA(cudaMemcpyAsync(lm->d_seq_len + r0, seq.data(), rpu * 4, cudaMemcpyHostToDevice, s));
+    SSRB_CUDA(cudaStreamSynchronize(s));
+    std::vector<RowPlan> chunk; int tok = 0;
+    for (int j = 0; j < rpu; j++) {
+        const int len = text_len + prompt_len + 1;
+        if (tok + len > lm->cfg.max_prefill_tokens) { SSRB_TRY(prefill_chunk(lm, chunk, &b, s, nullptr)); chunk.clear(); tok = 0; }
+        chunk.push_back({r0 + j, utt, text_len, prompt_len, len}); tok += len;
+    }
+    if (!chunk.empty()) SSRB_TRY(prefill_chunk(lm, chunk, &b, s, nullptr));
+    SSRB_TRY(heads_on_rows(lm, r0, rpu, s));
+    SSRB_TRY(launch_sample(lm->logits, lm->d_state, lm->d_seq_len, lm->d_next_tok, lm->d_gen_tok, nullptr, lm->d_iter, lm->sp, s, utt));
+    return 0;
+}
+
+int ssrb_lm_poll_flags(ssrb_lm* lm, void* stream, int32_t* done_flags, int* n_iter) {
+    SSRB_CHECK(lm && lm->n_utt > 0 && done_flags, "no active batch");
+    cudaStream_t s = (cudaStream_t)stream;
+    std::vector<UttState> st(lm->n_utt);
+    int it = 0;
+    SSRB_CUDA(cudaMemcpyAsync(st.data(), lm->d_state, lm->n_utt * sizeof(UttState), cudaMemcpyDeviceToHost, s));
+    SSRB_CUDA(cudaMemcpyAsync(&it, lm->d_iter, 4, cudaMemcpyDeviceToHost, s));
+    SSRB_CUDA(cudaStreamSynchronize(s));
+    for (int u = 0; u < lm->n_utt; u++) done_flags[u] = st[u].done ? 1 : 0;
+    if (n_iter) *n_iter = it;
     return 0;
 }
 

@@ -569,8 +569,8 @@ __global__ void __launch_bounds__(SMP_T) sample_kernel(const float* __restrict__
     __shared__ int s_argmax0;
     __shared__ float s_bestv[SMP_W], s_amv[SMP_W];
     __shared__ int s_besti[SMP_W], s_ami[SMP_W];
-    const int u = blockIdx.x, k = blockIdx.y;
-    if (u == 0 && k == 0 && threadIdx.x == 0) atomicAdd(iter_counter, 1);
+    const int u = p.utt0 + blockIdx.x, k = blockIdx.y;
+    if (p.count_iter && blockIdx.x == 0 && k == 0 && threadIdx.x == 0) atomicAdd(iter_counter, 1);
     const UttState S = st[u];
     if (S.done) return;                                    // uniform over the cluster
     const int K = p.K, V = p.V;
@@ -678,7 +678,7 @@ __global__ void __launch_bounds__(SMP_T) sample_kernel(const float* __restrict__
         const int v = min(t + SMP_T * i, V - 1);
         if (nz) qn[i] = nz[v];
         else {
-            const uint32_t rb = philox_u32(p.seed, (uint32_t)v, (uint32_t)k, (uint32_t)S.n_tok, (uint32_t)u);
+            const uint32_t rb = philox_u32(p.seed, (uint32_t)v, (uint32_t)k, (uint32_t)S.n_tok, (uint32_t)S.rng_id);
             qn[i] = fmaxf(-logf(((float)rb + 0.5f) * 2.3283064365386963e-10f), 1e-30f);
         }
     }
@@ -755,11 +755,15 @@ __global__ void __launch_bounds__(SMP_T) sample_kernel(const float* __restrict__
 }
 
 int launch_sample(const float* logits, UttState* st, int* seq_len, int* next_tok, int* gen_tok, const float* noise,
-                  int* iter_counter, const SampleParams& p, cudaStream_t s) {
+                  int* iter_counter, const SampleParams& p_in, cudaStream_t s, int only_utt) {
+    SampleParams p = p_in;
     SSRB_CHECK(p.K == 4, "sample: n_codebooks must be 4");
     SSRB_CHECK(p.V <= SMP_T * SMP_NPT, "sample: audio vocabulary too large for the sampling kernel");
-    SSRB_TRY(launch_pdl(sample_kernel, dim3(p.n_utt, 4), dim3(SMP_T), 0, s, /*cluster_y=*/4, logits, st, seq_len, next_tok, gen_tok,
-                        noise, iter_counter, p));
+    // only_utt >= 0: the first sample of ONE freshly admitted utterance (continuous batching); not a loop iteration
+    p.utt0 = only_utt >= 0 ? only_utt : 0;
+    p.count_iter = only_utt >= 0 ? 0 : 1;
+    SSRB_TRY(launch_pdl(sample_kernel, dim3(only_utt >= 0 ? 1 : p.n_utt, 4), dim3(SMP_T), 0, s, /*cluster_y=*/4, logits, st, seq_len,
+                        next_tok, gen_tok, noise, iter_counter, p));
     return 0;
 }
 

@@ -14,6 +14,7 @@ struct UttState {
     int y_len;        // audio positions already in the KV cache
     int n_tok;        // iterations recorded so far (all spans)
     int span_len[SSRB_MAX_SPANS];
+    int rng_id;       // Philox stream of this utterance: its index in a plain batch, the request index under continuous batching
 };
 
 struct SampleParams {
@@ -26,6 +27,8 @@ struct SampleParams {
     unsigned long long seed;
     int max_steps;
     int n_utt;
+    int utt0;         // first utterance handled by this launch (blockIdx.x == 0); 0 for the decode loop
+    int count_iter;   // 1: this launch is one iteration of the loop (bumps the iteration counter)
 };
 
 // packed prompt position descriptor for the prefill embedding (host-built)
@@ -61,6 +64,6 @@ int launch_attn_prefill_mma(const float* qkv, int D, int H, const void* kcache, 
                             const int* row_ids, const int* row_start, const int* row_len, int max_len, void* out, cudaStream_t s);
 // CFG + logit rules + top-k/top-p + sample + state machine (models/ssr.py:690-754)
 int launch_sample(const float* logits, UttState* st, int* seq_len, int* next_tok, int* gen_tok, const float* noise,
-                  int* iter_counter, const SampleParams& p, cudaStream_t s);
+                  int* iter_counter, const SampleParams& p, cudaStream_t s, int only_utt = -1);
 
 }  // namespace ssrb

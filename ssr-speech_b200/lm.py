@@ -62,7 +62,7 @@ class SSR_Speech:
         self._sd: Optional[Dict[str, torch.Tensor]] = None
         self._device: Optional[torch.device] = None
         self._h = None           # ssrb_lm*
-        self._cap = None         # (max_rows, max_seq, max_prefill_tokens, max_steps)
+        self._cap = None         # (max_rows, max prompt positions s0, max_prefill_tokens, max_steps)
         self.training = False
         self.last_stats: Dict[str, float] = {}
         self.poll_every = 16     # decode iterations enqueued between two `done` polls
@@ -112,17 +112,21 @@ class SSR_Speech:
             self._cap = None
 
     # ---- engine management ----------------------------------------------------------------------------
-    def _ensure_engine(self, rows: int, max_seq: int, prefill_tokens: int, max_steps: int):
+    def _ensure_engine(self, rows: int, s0: int, prefill_tokens: int, max_steps: int):
+        """Engine capacity: `rows` transformer rows, prompts of up to `s0` positions (text + audio + <mts>), `max_steps` loop
+        iterations per utterance; the KV rows hold s0 + max_steps (+ slack) positions.  Grow-only: a rebuild keeps the
+        largest value of every dimension seen so far (max_seq is derived, so growing max_steps also grows the cache)."""
         if self._sd is None:
             raise RuntimeError("load_state_dict must be called before inference")
         if self._device is None:
             raise RuntimeError("call .to('cuda') before inference (no CPU fallback)")
         cap = self._cap
-        if self._h is not None and cap[0] >= rows and cap[1] >= max_seq and cap[2] >= prefill_tokens and cap[3] >= max_steps:
+        if self._h is not None and cap[0] >= rows and cap[1] >= s0 and cap[2] >= prefill_tokens and cap[3] >= max_steps:
             return
         if cap is not None:   # grow-only
-            rows, max_seq = max(rows, cap[0]), max(max_seq, cap[1])
+            rows, s0 = max(rows, cap[0]), max(s0, cap[1])
             prefill_tokens, max_steps = max(prefill_tokens, cap[2]), max(max_steps, cap[3])
+        max_seq = s0 + max_steps + 8
         self._destroy()
         lib = _lib.load()
         c = self.cfg
@@ -141,14 +145,14 @@ class SSR_Speech:
             n_pos = max(_PE_MIN, max_seq + 8)
             _lib.load_state_dict_into(lib.ssrb_lm_load_tensor, h, {"pe_table": sinusoid_table(n_pos, c.d_model)})
             _lib.check(lib.ssrb_lm_check_loaded(h), "ssrb_lm_check_loaded")
-        self._cap = (rows, max_seq, prefill_tokens, max_steps)
+        self._cap = (rows, s0, prefill_tokens, max_steps)
 
     def reserve(self, n_utt: int, text_len: int, prompt_frames: int, aug_text: bool = True, n_spans: int = 1):
         """Optional: pre-build the engine for a given batch geometry (weights upload + allocations)."""
         rpu = 2 if aug_text else 1
         steps = self._max_steps(text_len, prompt_frames + 8, n_spans)
         s0 = text_len + prompt_frames + 8
-        self._ensure_engine(n_utt * rpu, s0 + steps + 8, min(max(s0, 16384), max(s0, s0 * n_utt * rpu)), steps)
+        self._ensure_engine(n_utt * rpu, s0, min(max(s0, 16384), max(s0, s0 * n_utt * rpu)), steps)
 
     def _max_steps(self, x_len: int, prompt_len: int, n_spans: int) -> int:
         K = self.cfg.n_codebooks
@@ -181,6 +185,41 @@ class SSR_Speech:
             uncond_xs=None if _uncond_x is None else [_uncond_x], noise=_noise, device=y.device)
         return out[0]
 
+    def _host_prepare(self, x, y, mask_interval, prompt_x, prompt, aug_text, aug_context, uncond_x):
+        """Host-side prologue of one utterance (ssr.py:564-626): optional aug_context concatenation, span maths, delay
+        pattern, <mts> insertion; draws the uncond text of the CFG row like the reference (global CPU generator)."""
+        cfg, K = self.cfg, self.cfg.n_codebooks
+        x = x.detach().to("cpu", torch.int64).reshape(-1)
+        yk = y.detach().to("cpu", torch.int64)
+        assert yk.ndim == 2 and yk.shape[1] == K, yk.shape
+        y = yk.T.contiguous().numpy()                                    # [K, T]
+        mi = torch.as_tensor(mask_interval).detach().to("cpu", torch.int64).reshape(-1, 2)
+        context_len = int(sum(int(b) - int(a) for a, b in mi.tolist()))
+        use_ctx = bool(aug_context and context_len < 2 * 50)             # ssr.py:564-568
+        out_len = 0
+        if use_ctx:
+            p = prompt.detach().to("cpu", torch.int64).T.contiguous().numpy()
+            px = prompt_x.detach().to("cpu", torch.int64).reshape(-1)
+            out_len = p.shape[1]
+            y = np.concatenate([p, y], axis=1)                           # ssr.py:581,591
+            x = torch.cat([px, x], 0)                                    # ssr.py:583,592
+        # nn.Embedding raises on ids outside its table (embedding.py:22-48); the device gathers would read stray memory
+        if y.size and (y.min() < 0 or y.max() >= cfg.n_audio_tokens):
+            raise IndexError("index out of range in self (audio token id outside the embedding table)")
+        if x.numel() and (int(x.min()) < 0 or int(x.max()) >= cfg.n_text_tokens):
+            raise IndexError("index out of range in self (phoneme id outside the embedding table)")
+        prep = seq.prepare(cfg, y, mi.tolist(), out_len=out_len)
+        ux = None
+        if aug_text:
+            if uncond_x is not None:
+                ux = uncond_x.detach().to("cpu", torch.int64).reshape(-1)
+            else:   # same draw as the reference: global CPU generator (ssr.py:574)
+                ux = torch.randint(0, self.n_text_tokens, (1, x.shape[0]))[0]
+            assert ux.shape[0] == x.shape[0]
+            if int(ux.min()) < 0 or int(ux.max()) >= cfg.n_text_tokens:
+                raise IndexError("index out of range in self (phoneme id outside the embedding table)")
+        return prep, x, ux
+
     @torch.no_grad()
     def open_batch(self, xs: List[torch.Tensor], ys: List[torch.Tensor], mask_intervals: List, prompt_xs=None,
                    prompts=None, top_k: int = -100, top_p: float = 1.0, temperature: float = 1.0,
@@ -203,30 +242,13 @@ class SSR_Speech:
         rpu = 2 if aug_text else 1
         preps, rows_text, x_lens = [], [], []
         for i in range(U):
-            x = xs[i].detach().to("cpu", torch.int64).reshape(-1)
-            yk = ys[i].detach().to("cpu", torch.int64)
-            assert yk.ndim == 2 and yk.shape[1] == K, yk.shape
-            y = yk.T.contiguous().numpy()                                    # [K, T]
-            mi = torch.as_tensor(mask_intervals[i]).detach().to("cpu", torch.int64).reshape(-1, 2)
-            context_len = int(sum(int(b) - int(a) for a, b in mi.tolist()))
-            use_ctx = bool(aug_context and context_len < 2 * 50)             # ssr.py:564-568
-            out_len = 0
-            if use_ctx:
-                p = prompts[i].detach().to("cpu", torch.int64).T.contiguous().numpy()
-                px = prompt_xs[i].detach().to("cpu", torch.int64).reshape(-1)
-                out_len = p.shape[1]
-                y = np.concatenate([p, y], axis=1)                           # ssr.py:581,591
-                x = torch.cat([px, x], 0)                                    # ssr.py:583,592
-            prep = seq.prepare(cfg, y, mi.tolist(), out_len=out_len)
+            prep, x, ux = self._host_prepare(xs[i], ys[i], mask_intervals[i], None if prompt_xs is None else prompt_xs[i],
+                                             None if prompts is None else prompts[i], aug_text, aug_context,
+                                             None if uncond_xs is None else uncond_xs[i])
             preps.append(prep)
             x_lens.append(int(x.shape[0]))
             rows_text.append(x)
             if aug_text:
-                if uncond_xs is not None:
-                    ux = uncond_xs[i].detach().to("cpu", torch.int64).reshape(-1)
-                else:   # same draw as the reference: global CPU generator (ssr.py:574)
-                    ux = torch.randint(0, self.n_text_tokens, (1, x.shape[0]))[0]
-                assert ux.shape[0] == x.shape[0]
                 rows_text.append(ux)
         R = U * rpu
         Lmax = max(x_lens)
@@ -234,7 +256,7 @@ class SSR_Speech:
         steps = max(self._max_steps(x_lens[i], preps[i].prompt_tokens.shape[1], preps[i].num_spans) for i in range(U))
         s0s = [x_lens[i] + preps[i].prompt_tokens.shape[1] + 1 for i in range(U)]
         total_prefill = sum(s0s) * rpu
-        self._ensure_engine(R, max(s0s) + steps + 8, max(max(s0s), min(total_prefill, 16384)), steps)
+        self._ensure_engine(R, max(s0s), max(max(s0s), min(total_prefill, 16384)), steps)
         lib = _lib.load()
         text = np.zeros((R, Lmax), dtype=np.int32)
         for r, t in enumerate(rows_text):
@@ -299,20 +321,92 @@ class SSR_Speech:
             self.last_stats = {"prefill_ms": ob["ev0"].elapsed_time(ob["ev1"]), "decode_ms": ob["ev1"].elapsed_time(ev2),
                                "iterations": it.value}
             results = []
-            buf = np.zeros((self._cap[3], K), dtype=np.int32)
-            span_len = (C.c_int32 * _lib.MAX_SPANS)()
-            n_tok = C.c_int(0)
             for i in range(U):
-                _lib.check(lib.ssrb_lm_read_tokens(self._h, st, i, C.c_void_p(buf.ctypes.data), buf.shape[0],
-                                                   C.byref(n_tok), span_len), "ssrb_lm_read_tokens")
-                toks = buf[:n_tok.value].astype(np.int64)
-                spans, o = [], 0
-                for s in range(preps[i].num_spans):
-                    spans.append(toks[o:o + span_len[s]])
-                    o += span_len[s]
-                res, marks, masks, nmi = seq.finalize(cfg, preps[i], spans)
-                results.append((torch.from_numpy(res).unsqueeze(0).to(dev if dev is not None else self._device),
-                                torch.from_numpy(marks).unsqueeze(0), masks, nmi))
+                res, marks, masks, nmi = self._collect(i, preps[i])
+                results.append((res.to(dev) if dev is not None else res, marks, masks, nmi))
+        return results
+
+    def _collect(self, slot: int, prep):
+        """Reads the sampled tokens of one finished slot and runs the epilogue (ssr.py:774-812)."""
+        lib, K = _lib.load(), self.cfg.n_codebooks
+        buf = np.zeros((self._cap[3], K), dtype=np.int32)
+        span_len = (C.c_int32 * _lib.MAX_SPANS)()
+        n_tok = C.c_int(0)
+        _lib.check(lib.ssrb_lm_read_tokens(self._h, _lib.stream_ptr(), slot, C.c_void_p(buf.ctypes.data), buf.shape[0],
+                                           C.byref(n_tok), span_len), "ssrb_lm_read_tokens")
+        toks = buf[:n_tok.value].astype(np.int64)
+        spans, o = [], 0
+        for s in range(prep.num_spans):
+            spans.append(toks[o:o + span_len[s]])
+            o += span_len[s]
+        res, marks, masks, nmi = seq.finalize(self.cfg, prep, spans)
+        return torch.from_numpy(res).unsqueeze(0).to(self._device), torch.from_numpy(marks).unsqueeze(0), masks, nmi
+
+    @torch.no_grad()
+    def serve(self, xs, ys, mask_intervals, max_slots: int, poll_every: Optional[int] = None, prompt_xs=None, prompts=None,
+              uncond_xs=None, seed: Optional[int] = None, aug_text: bool = False, aug_context: bool = False, **kw):
+        """Continuous batching: N requests through `max_slots` resident utterance slots.  The reference loops
+        over utterances one at a time (inference_v2.py:331-333); here a slot whose utterance has emitted its last EOG is
+        read back and refilled with the next request (ssrb_lm_admit: prefill into the slot's KV rows + first sample)
+        while the other slots keep decoding.  Request i samples from Philox stream i whatever slot it lands in, so the
+        result equals `inference_batch` over all N requests with the same seed (bit-exact in fp32 mode, where a row's
+        arithmetic does not depend on its batch).  Returns the per-request tuples of `inference_batch`, in request order."""
+        N = len(xs)
+        assert N == len(ys) == len(mask_intervals) and N > 0 and max_slots > 0
+        S = min(int(max_slots), N)
+        rpu = 2 if aug_text else 1
+        # host prologue of every request up front, in request order (the uncond-text draws consume the global CPU
+        # generator in the same order as one big batch would)
+        hp = [self._host_prepare(xs[i], ys[i], mask_intervals[i], None if prompt_xs is None else prompt_xs[i],
+                                 None if prompts is None else prompts[i], aug_text, aug_context,
+                                 None if uncond_xs is None else uncond_xs[i]) for i in range(N)]
+        x_lens = [int(h[1].shape[0]) for h in hp]
+        p_lens = [h[0].prompt_tokens.shape[1] for h in hp]
+        steps = max(self._max_steps(x_lens[i], p_lens[i], hp[i][0].num_spans) for i in range(N))
+        s0 = max(x_lens[i] + p_lens[i] + 1 for i in range(N))
+        if self._device is None:
+            self.to("cuda")
+        self._ensure_engine(S * rpu, s0, max(s0, min(s0 * S * rpu, 16384)), steps)
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
+        ob = self.open_batch(xs[:S], ys[:S], mask_intervals[:S], prompt_xs=None if prompt_xs is None else prompt_xs[:S],
+                             prompts=None if prompts is None else prompts[:S], aug_text=aug_text, aug_context=aug_context,
+                             uncond_xs=[h[2] for h in hp[:S]] if aug_text else None, seed=seed, **kw)
+        lib = _lib.load()
+        poll_every = int(poll_every or self.poll_every)
+        results = [None] * N
+        slot_req = list(range(S))           # request held by each slot (-1: empty)
+        nxt, n_left = S, N
+        flags = np.zeros(S, dtype=np.int32)
+        it = C.c_int(0)
+        limit = (N // S + 2) * (steps + 1) + 16
+        with torch.cuda.device(self._device):
+            st = _lib.stream_ptr()
+            while n_left > 0:
+                _lib.check(lib.ssrb_lm_poll_flags(self._h, st, C.c_void_p(flags.ctypes.data), C.byref(it)), "ssrb_lm_poll_flags")
+                for slot in range(S):
+                    r = slot_req[slot]
+                    if r < 0 or not flags[slot]:
+                        continue
+                    results[r] = self._collect(slot, hp[r][0])
+                    n_left -= 1
+                    slot_req[slot] = -1
+                    if nxt < N:
+                        prep, x, ux = hp[nxt]
+                        text = np.stack([x.numpy()] + ([ux.numpy()] if aug_text else [])).astype(np.int32)
+                        prom = np.ascontiguousarray(prep.prompt_tokens, dtype=np.int32)
+                        _lib.check(lib.ssrb_lm_admit(self._h, slot, C.c_void_p(text.ctypes.data), int(text.shape[1]),
+                                                     C.c_void_p(prom.ctypes.data), int(prom.shape[1]), int(prep.num_spans),
+                                                     int(nxt), st), "ssrb_lm_admit")
+                        slot_req[slot] = nxt
+                        nxt += 1
+                if n_left == 0:
+                    break
+                if it.value > limit:
+                    raise RuntimeError("serve: iteration limit exceeded")
+                _lib.check(lib.ssrb_lm_decode(self._h, poll_every, st), "ssrb_lm_decode")
+            torch.cuda.synchronize()
+        self.last_stats = {"iterations": it.value}
         return results
 
     # ---- test hooks -------------------------------------------------------------------------------------------
@@ -323,7 +417,7 @@ class SSR_Speech:
         Lx, Ty = int(x.shape[0]), int(audio_tokens.shape[1])
         if self._device is None:
             self.to("cuda")
-        self._ensure_engine(2, Lx + Ty + 16, Lx + Ty + 16, 8)
+        self._ensure_engine(2, Lx + Ty + 8, Lx + Ty + 16, 8)
         xt = x.detach().to("cpu", torch.int32).contiguous().numpy()
         at = audio_tokens.detach().to("cpu", torch.int32).contiguous().numpy()
         out = np.zeros((Ty, K, V), dtype=np.float32)

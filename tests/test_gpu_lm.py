@@ -149,6 +149,12 @@ def test_reference_assertions(model_fp32):
         model_fp32.inference(x, torch.tensor([5]), x, torch.tensor([5]), y, y, mask_interval=torch.tensor([[[10, 10]]]), cfg_coef=0.5)
     with pytest.raises(AssertionError):
         model_fp32.inference(x, torch.tensor([5]), x, torch.tensor([5]), y[..., :3], y, mask_interval=torch.tensor([[[10, 10]]]))
+    # ids outside the embedding tables: nn.Embedding raises IndexError in the reference (embedding.py:22-48)
+    with pytest.raises(IndexError):
+        model_fp32.inference(x, torch.tensor([5]), x, torch.tensor([5]), y + cfg_tiny().n_audio_tokens, y,
+                             mask_interval=torch.tensor([[[10, 10]]]))
+    with pytest.raises(IndexError):
+        model_fp32.inference(x + 500, torch.tensor([5]), x, torch.tensor([5]), y, y, mask_interval=torch.tensor([[[10, 10]]]))
 
 
 def test_sampling_distribution_top_p(model_fp32):
@@ -164,3 +170,36 @@ def test_sampling_distribution_top_p(model_fp32):
         raw = model_fp32.last_raw_logits()
         seen.add(s)
     assert len(seen) == 24 and torch.isfinite(raw[0]).all()
+
+
+def test_continuous_batching_equals_one_big_batch(model_fp32):
+    """serve(): 7 ragged requests (TTS, 1- and 2-span edits, CFG, top-p sampling) through 3 slots == the same requests
+    decoded as one batch with the same seed (request i owns Philox stream i whatever slot it lands in)."""
+    g = torch.Generator().manual_seed(21)
+    lens = [(9, 40), (12, 70), (7, 33), (10, 90), (11, 64), (8, 25), (13, 55)]
+    xs = [torch.randint(0, 100, (n,), generator=g) for n, _ in lens]
+    ys = [torch.randint(0, cfg_tiny().audio_vocab_size, (t, 4), generator=g) for _, t in lens]
+    spans = [[[40, 40]], [[10, 30]], [[33, 33]], [[20, 50]], [[5, 9], [30, 40]], [[25, 25]], [[0, 12]]]
+    un = [torch.randint(0, 101, (x.shape[0],), generator=g) for x in xs]
+    kw = dict(top_k=0, top_p=0.9, temperature=1.0, stop_repetition=2, cfg_coef=1.5, cfg_stride=2, aug_text=True, seed=77)
+    want = model_fp32.inference_batch(xs, ys, spans, uncond_xs=un, **kw)
+    got = model_fp32.serve(xs, ys, spans, max_slots=3, uncond_xs=un, poll_every=4, **kw)
+    assert len(got) == len(want) == 7
+    for (r0, m0, k0, n0), (r1, m1, k1, n1) in zip(want, got):
+        assert torch.equal(r0.cpu(), r1.cpu()) and torch.equal(m0, m1) and list(k0) == list(k1) and list(n0) == list(n1)
+    # one slot: plain sequential decoding, like the reference's loop over utterances (inference_v2.py:331-333)
+    seq1 = model_fp32.serve(xs[:3], ys[:3], spans[:3], max_slots=1, uncond_xs=un[:3], **kw)
+    for (r0, *_), (r1, *_) in zip(want[:3], seq1):
+        assert torch.equal(r0.cpu(), r1.cpu())
+
+
+def test_continuous_batching_bf16_runs(model_bf16):
+    g = torch.Generator().manual_seed(22)
+    xs = [torch.randint(0, 100, (8 + i,), generator=g) for i in range(5)]
+    ys = [torch.randint(0, cfg_tiny().audio_vocab_size, (30 + 7 * i, 4), generator=g) for i in range(5)]
+    spans = [[[y.shape[0], y.shape[0]]] for y in ys]
+    out = model_bf16.serve(xs, ys, spans, max_slots=2, top_k=0, top_p=0.8, stop_repetition=2, cfg_coef=1.5, cfg_stride=5,
+                           aug_text=True, seed=3)
+    for (res, marks, masks, nmi), y in zip(out, ys):
+        assert res.shape[1] == 4 and res.shape[2] >= y.shape[0] and int(res.max()) < cfg_tiny().n_audio_tokens   # an immediate EOG is legal
+        assert np.array_equal(res[0, :, :y.shape[0]].cpu().numpy(), y.numpy().T)

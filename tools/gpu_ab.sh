@@ -1,10 +1,15 @@
 #!/bin/bash
-# A/B of scheduling switches on the bench workload (no CPU baseline), after the GEMM / mode tests.
+# A/B of environment switches on the bench workload (no CPU baseline):  tools/gpu_ab.sh name:VAR=val,VAR2=val ...
+# Optional first: PYTEST="tests/test_gpu_modes.py ..." to run tests before; TIMELINE=1 dumps the in-kernel timeline of each variant.
 set -u
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_gemm.py tests/test_gpu_modes.py tests/test_gpu_lm.py -m gpu -x -q > gpurun_out/pytest_ab.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_ab.log
-tail -4 gpurun_out/pytest_ab.log
-run() { name=$1; shift; env "$@" timeout 400 python bench.py --no-cpu-baseline --steps 2 --warmup 3 > gpurun_out/ab_$name.json 2> gpurun_out/ab_$name.err; echo "$name rc=$?"; python - <<PY
+if [ -n "${PYTEST:-}" ]; then
+  timeout 900 python -m pytest $PYTEST -m gpu -x -q > gpurun_out/pytest_ab.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_ab.log
+  tail -4 gpurun_out/pytest_ab.log
+fi
+run() { name=$1; shift
+  if [ "${TIMELINE:-0}" = "1" ]; then env "$@" timeout 300 python tools/timeline.py --out gpurun_out/tl_$name.npy > gpurun_out/tl_$name.txt 2>&1; tail -1 gpurun_out/tl_$name.txt; fi
+  env "$@" timeout 400 python bench.py --no-cpu-baseline --steps 2 --warmup 3 ${BENCH_ARGS:-} > gpurun_out/ab_$name.json 2> gpurun_out/ab_$name.err; echo "$name rc=$?"; python - <<PY
 import json
 try:
     d=json.loads(open("gpurun_out/ab_$name.json").read().strip().splitlines()[-1])
