@@ -52,7 +52,6 @@ size_t attn_decode_ws_floats(int R, int H, int Smax);
 // bf16 production path (attn_decode_tma.cu): bulk-async staged K/V tiles; also appends this step's K/V row in place
 int launch_attn_decode_tma(const float* qkv, int R, int D, int H, void* kcache, void* vcache, int Smax, const int* seq_len,
                            const UttState* st, int rpu, float* ws, int* tickets, void* out, int prefetch, cudaStream_t s);
-int attn_decode_tma_nsplit(int R, int H, int Smax);
 int attn_decode_tma_max_nsplit(int Smax);
 int attn_decode_nsplit(int Smax);
 // causal attention over packed prompt rows (prefill); K/V read from the cache
