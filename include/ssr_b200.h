@@ -205,6 +205,16 @@ int ssrb_debug_timeline(unsigned long long* dev_buf, unsigned int* dev_idx, unsi
 int ssrb_op_gemm(const void* A_dev, const void* W_dev, const float* bias_dev, const float* residual_dev,
                  float* C_dev, int M, int N, int K, int dtype, int act, int impl, void* stream);
 
+/* The folded-LayerNorm GEMM pair exactly as the bf16 decode chain runs it (stands in for transformer.py:58-75 LayerNorm
+ * followed by the F.linear of activation.py:86 / transformer.py:386 / ssr.py:688):
+ *   stage 1  X = A1 . W1^T + bias1 + residual            (fp32 X_out [M,D]; the kernel also emits bf16(X) and the
+ *                                                          per-128-column {mean, M2} partials of every row)
+ *   stage 2  C = act(LayerNorm(X; gamma, beta, 1e-5) . W2^T + bias2)     LayerNorm applied in the GEMM epilogue
+ * A1 [M,K1], W1 [D,K1], W2 [N,D] bf16; M <= 128, D % 128 == 0, D <= 2048. */
+int ssrb_op_gemm_ln(const void* A1_dev, const void* W1_dev, const float* bias1_dev, const float* residual_dev,
+                    float* X_out_dev, int M, int D, int K1, const void* W2_dev, const float* gamma_dev,
+                    const float* beta_dev, const float* bias2_dev, float* C_out_dev, int N, int act, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

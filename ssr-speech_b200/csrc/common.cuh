@@ -188,6 +188,15 @@ struct GemmArgs {
     // grouped GEMM (blockIdx.z): element strides between groups
     int groups = 1;
     int64_t a_gs = 0, w_gs = 0, bias_gs = 0, c_gs = 0;
+    // ---- LayerNorm folded into the decode GEMMs (tcgen05 swap-AB path only, M <= 128, groups == 1) -----------------
+    // consumer: A holds bf16(x) (NOT normalised), W holds bf16(gamma_k * W_nk), bias holds b_n + sum_k beta_k W_nk and
+    //   C = act(rstd_r * (A.W^T - mean_r * ln_colsum_n) + bias) (+ residual); the row statistics are combined in a fixed
+    //   order from ln_blocks per-128-column partials {mean, M2} written by the kernel that produced x.
+    const float2* ln_part = nullptr; int ln_blocks = 0; const float* ln_colsum = nullptr; float ln_eps = 1e-5f;
+    int part_ld = 0;                                    // rows per block of the partial buffer, laid out [block][part_ld]
+    // producer: besides C (fp32, the residual stream) also write C2 = bf16(C) and the {mean, M2} partial of every
+    //   (row, 128-column block) into part_out[block * part_ld + row]
+    void* C2 = nullptr; int64_t ldc2 = 0; float2* part_out = nullptr;
 };
 
 int gemm_simt(const GemmArgs& g, cudaStream_t stream);

@@ -46,7 +46,13 @@ struct TcParams {
     const float* residual; long long ldr;
     void* C; long long ldc, c_gs; int c_dtype;
     int act;
+    // LayerNorm folded into the GEMM (see GemmArgs): consumer side / producer side
+    const float2* ln_part; int ln_blocks; const float* ln_colsum; float ln_eps;
+    bf16* C2; long long ldc2; float2* part_out;
+    int part_ld;       // partials are stored [block][part_ld rows]: one coalesced read per block in the consumer
 };
+constexpr int LN_BLOCK = 128;          // columns per {mean, M2} partial
+constexpr int LN_MAX_BLOCKS = 16;      // d_model <= 2048
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -134,6 +140,8 @@ __global__ void __launch_bounds__(192, 2) gemm_tc_kernel(const __grid_constant__
 
     pdl_launch_dependents();
     __shared__ int s_ts;
+    __shared__ float s_mu[P_ROWS], s_rs[P_ROWS];           // folded LayerNorm: mean / rstd of every activation row
+    __shared__ float2 s_wp[4][P_ROWS];                      // producer side, unclustered: per-warp {mean, M2} of 32 columns
     const int ts = ts_begin(TSK_GEMM);
     if (threadIdx.x == 0) s_ts = ts;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -226,6 +234,30 @@ __global__ void __launch_bounds__(192, 2) gemm_tc_kernel(const __grid_constant__
     } else {
         // ===== epilogue: TMEM -> registers -> (smem partial | global) =====
         pdl_wait();                                       // residual / output buffers belong to the kernel chain
+        if (SWAP && prm.ln_part) {
+            // folded LayerNorm: combine the per-block {mean, M2} partials of every activation row (fixed order, Chan's
+            // formula with equal block sizes) while the TMA/MMA pipeline is still running
+            if (nl < prm.M) {
+                // [block][row] layout: a warp reads 32 consecutive rows of one block in one 256-byte request (every CTA of
+                // the grid reads the same few KB — per-row gathers made this an L2 hot spot worth 2.5 us per GEMM)
+                const float2* pp = prm.ln_part + nl;
+                float2 pb[LN_MAX_BLOCKS];
+#pragma unroll
+                for (int b = 0; b < LN_MAX_BLOCKS; b++)
+                    pb[b] = b < prm.ln_blocks ? __ldcg(pp + (long long)b * prm.part_ld) : make_float2(0.f, 0.f);
+                float ms = 0.f;
+#pragma unroll
+                for (int b = 0; b < LN_MAX_BLOCKS; b++) ms += pb[b].x;
+                const float mean = ms / (float)prm.ln_blocks;
+                float m2 = 0.f;
+#pragma unroll
+                for (int b = 0; b < LN_MAX_BLOCKS; b++)
+                    if (b < prm.ln_blocks) { const float d = pb[b].x - mean; m2 += pb[b].y + (float)LN_BLOCK * d * d; }
+                s_mu[nl] = mean;
+                s_rs[nl] = rsqrtf(m2 / (float)(LN_BLOCK * prm.ln_blocks) + prm.ln_eps);
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
         if (nk > 0) {
             mbar_wait(accum_bar, 0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -236,6 +268,7 @@ __global__ void __launch_bounds__(192, 2) gemm_tc_kernel(const __grid_constant__
             const bool nok = n < prm.N;
             if (!clustered) {
                 const float bv = (prm.bias && nok) ? prm.bias[grp * prm.bias_gs + n] : 0.f;
+                const float cn = (prm.ln_part && nok) ? prm.ln_colsum[n] : 0.f;
 #pragma unroll 1
                 for (int c0 = 0; c0 < QROWS; c0 += 16) {
                     if (c0 >= prm.M) break;
@@ -247,12 +280,32 @@ __global__ void __launch_bounds__(192, 2) gemm_tc_kernel(const __grid_constant__
 #pragma unroll
                     for (int j = 0; j < 16; j++) {
                         const int r = c0 + j;
-                        if (r < prm.M && nok) {
-                            const float x = apply_act(v[j] + bv, prm.act) + resv[j];
+                        if (r >= prm.M) continue;         // CTA-uniform
+                        float a = v[j];
+                        if (prm.ln_part) a = s_rs[r] * (a - s_mu[r] * cn);
+                        const float x = nok ? apply_act(a + bv, prm.act) + resv[j] : 0.f;
+                        if (nok) {
                             const long long o = grp * prm.c_gs + (long long)r * prm.ldc + n;
                             if (prm.c_dtype == SSRB_DTYPE_F32) reinterpret_cast<float*>(prm.C)[o] = x;
                             else reinterpret_cast<bf16*>(prm.C)[o] = __float2bfloat16_rn(x);
+                            if (prm.C2) prm.C2[(long long)r * prm.ldc2 + n] = __float2bfloat16_rn(x);
                         }
+                        if (prm.part_out) {               // N % 128 == 0 here: every lane holds a real column
+                            const float mw = warp_sum(x) * (1.f / 32.f);
+                            const float d = x - mw;
+                            const float q = warp_sum(d * d);
+                            if (lane == 0) s_wp[lg][r] = make_float2(mw, q);
+                        }
+                    }
+                }
+                if (prm.part_out) {
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (nl < prm.M) {                      // 4 warps x 32 columns -> one 128-column partial (fixed order)
+                        const float2 p0 = s_wp[0][nl], p1 = s_wp[1][nl], p2 = s_wp[2][nl], p3 = s_wp[3][nl];
+                        const float mean = (p0.x + p1.x + p2.x + p3.x) * 0.25f;
+                        const float d0 = p0.x - mean, d1 = p1.x - mean, d2 = p2.x - mean, d3 = p3.x - mean;
+                        const float m2 = (p0.y + 32.f * d0 * d0) + (p1.y + 32.f * d1 * d1) + (p2.y + 32.f * d2 * d2) + (p3.y + 32.f * d3 * d3);
+                        prm.part_out[(long long)blockIdx.x * prm.part_ld + nl] = make_float2(mean, m2);
                     }
                 }
             } else {
@@ -328,8 +381,9 @@ __global__ void __launch_bounds__(192, 2) gemm_tc_kernel(const __grid_constant__
             const int ew = warp - 2;
             const int n = p_row0 + 4 * lane;
             if (n < prm.N) {                                              // N % 4 == 0 (checked on the host)
-                float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), c4 = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (prm.bias) bv = *reinterpret_cast<const float4*>(prm.bias + grp * prm.bias_gs + n);
+                if (prm.ln_part) c4 = *reinterpret_cast<const float4*>(prm.ln_colsum + n);
                 uint32_t rbase[MAX_SPLITS];                                // this CTA's tile address inside every peer
 #pragma unroll
                 for (int s = 0; s < MAX_SPLITS; s++)
@@ -369,7 +423,12 @@ __global__ void __launch_bounds__(192, 2) gemm_tc_kernel(const __grid_constant__
                     for (int j = 0; j < 2; j++) {
                         const int r = r0 + j * 4 * prm.splits;
                         if (r >= prm.M) continue;
-                        const float4 acc = acc4[j];
+                        float4 acc = acc4[j];
+                        if (prm.ln_part) {
+                            const float mu = s_mu[r], rs = s_rs[r];
+                            acc.x = rs * (acc.x - mu * c4.x); acc.y = rs * (acc.y - mu * c4.y);
+                            acc.z = rs * (acc.z - mu * c4.z); acc.w = rs * (acc.w - mu * c4.w);
+                        }
                         float4 x;
                         x.x = apply_act(acc.x + bv.x, prm.act) + resv[j].x; x.y = apply_act(acc.y + bv.y, prm.act) + resv[j].y;
                         x.z = apply_act(acc.z + bv.z, prm.act) + resv[j].z; x.w = apply_act(acc.w + bv.w, prm.act) + resv[j].w;
@@ -379,6 +438,26 @@ __global__ void __launch_bounds__(192, 2) gemm_tc_kernel(const __grid_constant__
                             __nv_bfloat162 lo = __floats2bfloat162_rn(x.x, x.y), hi = __floats2bfloat162_rn(x.z, x.w);
                             uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&lo); pk.y = *reinterpret_cast<uint32_t*>(&hi);
                             *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(prm.C) + o) = pk;
+                        }
+                        if (prm.C2) {
+                            __nv_bfloat162 lo = __floats2bfloat162_rn(x.x, x.y), hi = __floats2bfloat162_rn(x.z, x.w);
+                            uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&lo); pk.y = *reinterpret_cast<uint32_t*>(&hi);
+                            *reinterpret_cast<uint2*>(prm.C2 + (long long)r * prm.ldc2 + n) = pk;
+                        }
+                        if (prm.part_out) {               // N % 128 == 0: the warp holds one full 128-column block of row r
+                            // one pass, shifted by the block's first element (sum and sum of squares of x - x0 reduce
+                            // together: 6 dependent shuffles instead of 10 on the kernel's exit path)
+                            const float x0 = __shfl_sync(0xffffffffu, x.x, 0);
+                            const float dx = x.x - x0, dy = x.y - x0, dz = x.z - x0, dw = x.w - x0;
+                            float s1 = (dx + dy) + (dz + dw), s2 = (dx * dx + dy * dy) + (dz * dz + dw * dw);
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) {
+                                s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+                            }
+                            if (lane == 0)
+                                prm.part_out[(long long)blockIdx.x * prm.part_ld + r] =
+                                    make_float2(x0 + s1 * (1.f / (float)LN_BLOCK), fmaxf(s2 - s1 * s1 * (1.f / (float)LN_BLOCK), 0.f));
                         }
                     }
                 }
@@ -652,6 +731,16 @@ int gemm_tc(const GemmArgs& g, void*, size_t, cudaStream_t s) {
     prm.M = g.M; prm.N = g.N; prm.K = g.K; prm.nkb = g.K / BK;
     prm.bias = g.bias; prm.bias_gs = g.bias_gs; prm.residual = g.residual; prm.ldr = g.ldr;
     prm.C = g.C; prm.ldc = g.ldc; prm.c_gs = g.c_gs; prm.c_dtype = g.c_dtype; prm.act = g.act;
+    if (g.ln_part || g.C2 || g.part_out) {
+        SSRB_CHECK(g.M <= 128 && g.groups == 1, "folded LayerNorm needs the swap-AB decode path (M <= 128, one group)");
+        SSRB_CHECK(!g.ln_part || (g.ln_colsum && g.ln_blocks >= 1 && g.ln_blocks <= LN_MAX_BLOCKS && g.K == g.ln_blocks * LN_BLOCK),
+                   "folded LayerNorm: K must be ln_blocks x 128 <= 2048");
+        SSRB_CHECK((!g.part_out && !g.C2) || (g.N % LN_BLOCK == 0 && g.c_dtype == SSRB_DTYPE_F32 && g.ldc2 % 4 == 0),
+                   "row-statistics epilogue needs fp32 C and N % 128 == 0");
+    }
+    prm.ln_part = g.ln_part; prm.ln_blocks = g.ln_blocks; prm.ln_colsum = g.ln_colsum; prm.ln_eps = g.ln_eps;
+    prm.C2 = reinterpret_cast<bf16*>(g.C2); prm.ldc2 = g.ldc2; prm.part_out = g.part_out; prm.part_ld = g.part_ld;
+    SSRB_CHECK((!g.ln_part && !g.part_out) || g.part_ld >= g.M, "row-statistics buffer: part_ld must cover the M rows");
     const bf16* A = reinterpret_cast<const bf16*>(g.A);
     const bf16* W = reinterpret_cast<const bf16*>(g.W);
     if (g.M <= 128) {

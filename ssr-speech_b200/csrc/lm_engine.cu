@@ -24,6 +24,11 @@ bool pdl_enabled() {
 }
 
 // SSRB_ATTN_PREFETCH=0: the decode attention waits for the QKV GEMM before it starts streaming the cache
+// SSRB_LN_FOLD=0: keep the separate LayerNorm kernels in the decode chain (33 more launches per iteration)
+static bool ln_fold_enabled() {
+    static const bool on = [] { const char* e = getenv("SSRB_LN_FOLD"); return !(e && e[0] == '0'); }();
+    return on;
+}
 static bool attn_prefetch_enabled() {
     static const bool on = [] { const char* e = getenv("SSRB_ATTN_PREFETCH"); return !(e && e[0] == '0'); }();
     return on;
@@ -40,6 +45,10 @@ struct LayerW {
     void *wqkv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr;
     float *bqkv = nullptr, *bo = nullptr, *b1 = nullptr, *b2 = nullptr;
     float *ln1w = nullptr, *ln1b = nullptr, *ln2w = nullptr, *ln2b = nullptr;
+    // LayerNorm folded into the decode GEMMs: gamma-scaled copies of the matrices that consume a LayerNorm, their column
+    // sums and beta-shifted biases (fold_ln_kernel)
+    void *wqkv_f = nullptr, *w1_f = nullptr;
+    float *cqkv = nullptr, *bqkv_f = nullptr, *c1 = nullptr, *b1_f = nullptr;
 };
 
 }  // namespace ssrb
@@ -58,6 +67,11 @@ struct ssrb_lm {
     float alpha_t = 1.f, alpha_a = 1.f;
     void *hw1 = nullptr, *hw2 = nullptr;       // [K*Hh, D], [K][V, Hh]
     float *hb1 = nullptr, *hb2 = nullptr;
+    void* hw1_f = nullptr; float *hc1 = nullptr, *hb1_f = nullptr;   // final LayerNorm folded into the first head layer
+    bool fold_ok = false;      // the configuration supports the folded chain (bf16 tensor-core GEMMs, d_model <= 2048)
+    bool fold_dirty = true;    // weights changed since the folded copies were built
+    bool fold = false;         // the open batch decodes through the folded chain (R <= 128)
+    float2* ln_part = nullptr; // [max_rows][d_model / 128] {mean, M2} partials of the residual stream
     std::map<std::string, bool> loaded;
     // workspace
     int Mmax = 0;
@@ -133,6 +147,19 @@ int ssrb_lm_create(const ssrb_lm_config* c, int device, ssrb_lm** out) {
     SSRB_TRY(dev_alloc((void**)&lm->lnfw, D * 4)); SSRB_TRY(dev_alloc((void**)&lm->lnfb, D * 4));
     SSRB_TRY(dev_alloc(&lm->hw1, (size_t)K * Hh * D * e)); SSRB_TRY(dev_alloc(&lm->hw2, (size_t)K * V * Hh * e));
     SSRB_TRY(dev_alloc((void**)&lm->hb1, K * Hh * 4)); SSRB_TRY(dev_alloc((void**)&lm->hb2, K * V * 4));
+    lm->fold_ok = ln_fold_enabled() && c->weight_dtype == SSRB_DTYPE_BF16 && c->gemm_impl != 1 && D % 128 == 0 &&
+                  D <= 2048 && F % 128 == 0 && (K * Hh) % 4 == 0;
+    if (lm->fold_ok) {
+        for (int n = 0; n < L; n++) {
+            LayerW& w = lm->layers[n];
+            SSRB_TRY(dev_alloc(&w.wqkv_f, (size_t)3 * D * D * e)); SSRB_TRY(dev_alloc(&w.w1_f, (size_t)F * D * e));
+            SSRB_TRY(dev_alloc((void**)&w.cqkv, 3 * D * 4)); SSRB_TRY(dev_alloc((void**)&w.bqkv_f, 3 * D * 4));
+            SSRB_TRY(dev_alloc((void**)&w.c1, F * 4)); SSRB_TRY(dev_alloc((void**)&w.b1_f, F * 4));
+        }
+        SSRB_TRY(dev_alloc(&lm->hw1_f, (size_t)K * Hh * D * e));
+        SSRB_TRY(dev_alloc((void**)&lm->hc1, K * Hh * 4)); SSRB_TRY(dev_alloc((void**)&lm->hb1_f, K * Hh * 4));
+        SSRB_TRY(dev_alloc((void**)&lm->ln_part, (size_t)c->max_rows * (D / 128) * sizeof(float2)));
+    }
     // workspace
     const int R = c->max_rows;
     lm->Mmax = c->max_prefill_tokens > R ? c->max_prefill_tokens : R;
@@ -169,14 +196,15 @@ void ssrb_lm_destroy(ssrb_lm* lm) {
     cudaDeviceSynchronize();
     if (lm->graph) cudaGraphExecDestroy(lm->graph);
     for (auto& w : lm->layers) {
-        void* ps[] = {w.wqkv, w.wo, w.w1, w.w2, w.bqkv, w.bo, w.b1, w.b2, w.ln1w, w.ln1b, w.ln2w, w.ln2b};
+        void* ps[] = {w.wqkv, w.wo, w.w1, w.w2, w.bqkv, w.bo, w.b1, w.b2, w.ln1w, w.ln1b, w.ln2w, w.ln2b,
+                      w.wqkv_f, w.w1_f, w.cqkv, w.bqkv_f, w.c1, w.b1_f};
         for (void* p : ps) cudaFree(p);
     }
     void* ps[] = {lm->text_emb, lm->audio_emb, lm->pe, lm->lnfw, lm->lnfb, lm->hw1, lm->hw2, lm->hb1, lm->hb2, lm->x,
                   lm->qkv, lm->logits, lm->hn, lm->ao, lm->hid, lm->hlast, lm->hh, lm->kcache, lm->vcache, lm->attn_ws,
                   lm->tickets, lm->tc_ws, lm->d_desc, lm->d_rows, lm->d_slots, lm->d_row_ids, lm->d_row_start,
                   lm->d_row_len, lm->d_last_idx, lm->d_state, lm->d_seq_len, lm->d_next_tok, lm->d_gen_tok, lm->d_iter,
-                  lm->staging};
+                  lm->staging, lm->hw1_f, lm->hc1, lm->hb1_f, lm->ln_part};
     for (void* p : ps) cudaFree(p);
     delete lm;
 }
@@ -258,6 +286,21 @@ int ssrb_lm_load_tensor(ssrb_lm* lm, const char* name_c, const float* host, cons
         return 0;   // keys that carry no inference state (e.g. accuracy_metrics.*) are ignored
     }
     lm->loaded[name] = true;
+    lm->fold_dirty = true;
+    return 0;
+}
+
+// (re)build the gamma-folded copies of the LayerNorm-consuming matrices once all tensors are loaded
+static int fold_weights(ssrb_lm* lm, cudaStream_t s) {
+    if (!lm->fold_ok || !lm->fold_dirty) return 0;
+    const int D = lm->D, F = lm->F;
+    for (auto& w : lm->layers) {
+        SSRB_TRY(launch_fold_ln(w.wqkv, 3 * D, D, w.ln1w, w.ln1b, w.bqkv, w.wqkv_f, w.cqkv, w.bqkv_f, s));
+        SSRB_TRY(launch_fold_ln(w.w1, F, D, w.ln2w, w.ln2b, w.b1, w.w1_f, w.c1, w.b1_f, s));
+    }
+    SSRB_TRY(launch_fold_ln(lm->hw1, lm->K * lm->Hh, D, lm->lnfw, lm->lnfb, lm->hb1, lm->hw1_f, lm->hc1, lm->hb1_f, s));
+    SSRB_CUDA(cudaStreamSynchronize(s));
+    lm->fold_dirty = false;
     return 0;
 }
 
@@ -285,6 +328,7 @@ static int gemm(ssrb_lm* lm, GemmArgs g, cudaStream_t s) {
     g.ab_dtype = lm->wdt;
     if (lm->wdt == SSRB_DTYPE_BF16 && lm->cfg.gemm_impl != 1 && gemm_tc_supported(g))
         return gemm_tc(g, lm->tc_ws, lm->tc_ws_bytes, s);
+    SSRB_CHECK(!g.ln_part && !g.part_out && !g.C2, "folded LayerNorm needs the tcgen05 GEMM");
     return gemm_simt(g, s);
 }
 
@@ -325,6 +369,42 @@ static int run_layer(ssrb_lm* lm, int n, int M, bool prefill, int n_rows, int ma
     return 0;
 }
 
+// one decoder layer of a decode iteration with both LayerNorms folded into the GEMMs that consume them (gemm_tc.cu):
+// hn holds bf16(x), ln_part the row statistics of x; the two residual GEMMs refresh both while they write x.
+static int run_layer_fold(ssrb_lm* lm, int n, int M, cudaStream_t s) {
+    const int D = lm->D, F = lm->F, H = lm->H;
+    const LayerW& w = lm->layers[n];
+    const size_t e = lm->esz;
+    void* kc = (char*)lm->kcache + (size_t)n * lm->kv_layer_elems * e;
+    void* vc = (char*)lm->vcache + (size_t)n * lm->kv_layer_elems * e;
+    GemmArgs g;
+    g.A = lm->hn; g.lda = D; g.W = w.wqkv_f; g.ldw = D; g.bias = w.bqkv_f; g.C = lm->qkv; g.ldc = 3 * D;
+    g.M = M; g.N = 3 * D; g.K = D; g.c_dtype = SSRB_DTYPE_F32;
+    g.ln_part = lm->ln_part; g.part_ld = lm->cfg.max_rows; g.ln_blocks = D / 128; g.ln_colsum = w.cqkv;
+    SSRB_TRY(gemm(lm, g, s));
+    {
+        ProfScope ps(lm, PC_ATTN, s);
+        SSRB_TRY(launch_attn_decode(lm->qkv, M, D, H, kc, vc, lm->wdt, lm->cfg.max_seq, lm->d_seq_len, lm->d_state,
+                                    lm->rpu, lm->attn_ws, lm->tickets, lm->ao, lm->wdt, attn_prefetch_enabled() ? 1 : 0, s));
+    }
+    g = GemmArgs();
+    g.A = lm->ao; g.lda = D; g.W = w.wo; g.ldw = D; g.bias = w.bo; g.residual = lm->x; g.ldr = D; g.C = lm->x; g.ldc = D;
+    g.M = M; g.N = D; g.K = D; g.c_dtype = SSRB_DTYPE_F32;
+    g.C2 = lm->hn; g.ldc2 = D; g.part_out = lm->ln_part; g.part_ld = lm->cfg.max_rows;
+    SSRB_TRY(gemm(lm, g, s));
+    g = GemmArgs();
+    g.A = lm->hn; g.lda = D; g.W = w.w1_f; g.ldw = D; g.bias = w.b1_f; g.C = lm->hid; g.ldc = F;
+    g.M = M; g.N = F; g.K = D; g.act = ACT_RELU; g.c_dtype = lm->wdt;
+    g.ln_part = lm->ln_part; g.part_ld = lm->cfg.max_rows; g.ln_blocks = D / 128; g.ln_colsum = w.c1;
+    SSRB_TRY(gemm(lm, g, s));
+    g = GemmArgs();
+    g.A = lm->hid; g.lda = F; g.W = w.w2; g.ldw = F; g.bias = w.b2; g.residual = lm->x; g.ldr = D; g.C = lm->x; g.ldc = D;
+    g.M = M; g.N = D; g.K = F; g.c_dtype = SSRB_DTYPE_F32;
+    g.C2 = lm->hn; g.ldc2 = D; g.part_out = lm->ln_part; g.part_ld = lm->cfg.max_rows;
+    SSRB_TRY(gemm(lm, g, s));
+    return 0;
+}
+
 // final LN (gathered rows) + 4 prediction heads -> logits [M, K, V] fp32
 static int run_heads(ssrb_lm* lm, const int* gather_idx, int M, void* hl, void* hhbuf, float* logits, cudaStream_t s) {
     const int D = lm->D, K = lm->K, V = lm->V, Hh = lm->Hh;
@@ -342,11 +422,30 @@ static int run_heads(ssrb_lm* lm, const int* gather_idx, int M, void* hl, void* 
 }
 
 static int enqueue_step(ssrb_lm* lm, cudaStream_t s) {
+    if (lm->fold) {
+        { ProfScope ps(lm, PC_SMALL, s);
+          SSRB_TRY(launch_embed_step_fold(lm->d_next_tok, lm->d_state, lm->R, lm->rpu, lm->K, lm->D, lm->audio_emb, lm->V,
+                                          lm->pe, lm->alpha_a, lm->x, lm->hn, lm->ln_part, lm->cfg.max_rows, s)); }
+        for (int n = 0; n < lm->L; n++) SSRB_TRY(run_layer_fold(lm, n, lm->R, s));
+        // final LayerNorm folded into the first head layer
+        const int D = lm->D, K = lm->K, V = lm->V, Hh = lm->Hh;
+        GemmArgs g;
+        g.A = lm->hn; g.lda = D; g.W = lm->hw1_f; g.ldw = D; g.bias = lm->hb1_f; g.C = lm->hh; g.ldc = K * Hh;
+        g.M = lm->R; g.N = K * Hh; g.K = D; g.act = ACT_GELU; g.c_dtype = lm->wdt;
+        g.ln_part = lm->ln_part; g.part_ld = lm->cfg.max_rows; g.ln_blocks = D / 128; g.ln_colsum = lm->hc1;
+        SSRB_TRY(gemm(lm, g, s));
+        g = GemmArgs();
+        g.A = lm->hh; g.lda = K * Hh; g.a_gs = Hh; g.W = lm->hw2; g.ldw = Hh; g.w_gs = (int64_t)V * Hh;
+        g.bias = lm->hb2; g.bias_gs = V; g.C = lm->logits; g.ldc = (int64_t)K * V; g.c_gs = V;
+        g.M = lm->R; g.N = V; g.K = Hh; g.groups = K; g.c_dtype = SSRB_DTYPE_F32;
+        SSRB_TRY(gemm(lm, g, s));
+    } else {
     { ProfScope ps(lm, PC_SMALL, s);
       SSRB_TRY(launch_embed_step(lm->d_next_tok, lm->d_state, lm->R, lm->rpu, lm->K, lm->D, lm->audio_emb, lm->V, lm->pe,
                                  lm->alpha_a, lm->x, s)); }
     for (int n = 0; n < lm->L; n++) SSRB_TRY(run_layer(lm, n, lm->R, false, 0, 0, s));
     SSRB_TRY(run_heads(lm, nullptr, lm->R, lm->hlast, lm->hh, lm->logits, s));
+    }
     ProfScope ps(lm, PC_SAMPLE, s);
     SSRB_TRY(launch_sample(lm->logits, lm->d_state, lm->d_seq_len, lm->d_next_tok, lm->d_gen_tok, lm->noise, lm->d_iter,
                            lm->sp, s));
@@ -417,6 +516,8 @@ int ssrb_lm_begin(ssrb_lm* lm, const ssrb_lm_batch* b, const ssrb_sampling* sp, 
     SSRB_CHECK(sp->cfg_coef >= 1.0f, "cfg_coef must be >= 1.0");           // ssr.py:552
     SSRB_CHECK(sp->n_silence <= SSRB_MAX_SILENCE, "too many silence tokens");
     lm->n_utt = U; lm->rpu = rpu; lm->R = R; lm->noise = noise_dev;
+    SSRB_TRY(fold_weights(lm, s));
+    lm->fold = lm->fold_ok && R <= 128;
     if (lm->graph) { cudaGraphExecDestroy(lm->graph); lm->graph = nullptr; }
     SampleParams& p = lm->sp;
     p.K = K; p.V = lm->V; p.rpu = rpu; p.empty_token = lm->cfg.empty_token; p.eog = lm->cfg.eog; p.eos = lm->cfg.eos;
@@ -697,4 +798,32 @@ int ssrb_op_gemm(const void* A, const void* W, const float* bias, const float* r
         return gemm_tc(g, ws, wsb, (cudaStream_t)stream);
     }
     return gemm_simt(g, (cudaStream_t)stream);
+}
+
+int ssrb_op_gemm_ln(const void* A1, const void* W1, const float* bias1, const float* residual, float* X_out, int M, int D,
+                    int K1, const void* W2, const float* gamma, const float* beta, const float* bias2, float* C_out, int N,
+                    int act, void* stream) {
+    SSRB_CHECK(A1 && W1 && X_out && W2 && gamma && beta && C_out, "null argument");
+    SSRB_CHECK(D % 128 == 0 && D <= 2048 && M >= 1 && M <= 128, "op_gemm_ln: d_model must be a multiple of 128 <= 2048, M <= 128");
+    cudaStream_t s = (cudaStream_t)stream;
+    void *xb = nullptr, *w2f = nullptr; float *cs = nullptr, *bf = nullptr; float2* part = nullptr;
+    SSRB_CUDA(cudaMalloc(&xb, (size_t)M * D * 2)); SSRB_CUDA(cudaMalloc(&w2f, (size_t)N * D * 2));
+    SSRB_CUDA(cudaMalloc((void**)&cs, (size_t)N * 4)); SSRB_CUDA(cudaMalloc((void**)&bf, (size_t)N * 4));
+    SSRB_CUDA(cudaMalloc((void**)&part, (size_t)M * (D / 128) * sizeof(float2)));
+    int rc = launch_fold_ln(W2, N, D, gamma, beta, bias2, w2f, cs, bf, s);
+    GemmArgs g;
+    g.A = A1; g.lda = K1; g.W = W1; g.ldw = K1; g.bias = bias1; g.residual = residual; g.ldr = D; g.C = X_out; g.ldc = D;
+    g.M = M; g.N = D; g.K = K1; g.ab_dtype = SSRB_DTYPE_BF16; g.c_dtype = SSRB_DTYPE_F32;
+    g.C2 = xb; g.ldc2 = D; g.part_out = part; g.part_ld = M;
+    if (!rc) rc = gemm_tc_supported(g) ? gemm_tc(g, nullptr, 0, s) : 1;
+    g = GemmArgs();
+    g.A = xb; g.lda = D; g.W = w2f; g.ldw = D; g.bias = bf; g.C = C_out; g.ldc = N;
+    g.M = M; g.N = N; g.K = D; g.act = act; g.ab_dtype = SSRB_DTYPE_BF16; g.c_dtype = SSRB_DTYPE_F32;
+    g.ln_part = part; g.part_ld = M; g.ln_blocks = D / 128; g.ln_colsum = cs;
+    if (!rc) rc = gemm_tc_supported(g) ? gemm_tc(g, nullptr, 0, s) : 1;
+    cudaError_t ce = cudaStreamSynchronize(s);
+    cudaFree(xb); cudaFree(w2f); cudaFree(cs); cudaFree(bf); cudaFree(part);
+    if (rc) return rc;
+    SSRB_CUDA(ce);
+    return 0;
 }

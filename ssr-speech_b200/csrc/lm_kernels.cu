@@ -63,6 +63,88 @@ __global__ void __launch_bounds__(256) embed_step_kernel(const int* __restrict__
     ts_end(ts);
 }
 
+// Decode step with LayerNorm folded into the consuming GEMMs (gemm_tc.cu): besides the fp32 residual stream the kernel
+// writes bf16(x) — the GEMM operand — and the {mean, M2} partial of every 128-column block of the row.  Same per-element
+// arithmetic as embed_step_kernel; each thread owns 8 consecutive columns, 16 lanes own one block.
+__global__ void __launch_bounds__(256) embed_step_fold_kernel(const int* __restrict__ next_tok, const UttState* __restrict__ st,
+                                                              int rpu, int K, int D, const float* __restrict__ audio_emb, int V,
+                                                              const float* __restrict__ pe, float alpha_a, float* __restrict__ x,
+                                                              bf16* __restrict__ xb, float2* __restrict__ part, int part_ld) {
+    const int ts = ts_begin(TSK_EMBED);
+    pdl_wait();
+    pdl_launch_dependents();                      // see embed_step_kernel: released only after the previous iteration completed
+    ts_dep(ts);
+    const int r = blockIdx.x, u = r / rpu;
+    const int* tk = next_tok + u * K;
+    const int pos = st[u].y_len;
+    const int64_t tbl = (int64_t)V * D;
+    const int d0 = threadIdx.x * 8;
+    const bool valid = d0 < D;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = 0.f;
+    if (valid) {
+        float e0[8], e1[8], e2[8], e3[8], pr[8];
+        load8(audio_emb + (int64_t)tk[0] * D + d0, e0);
+        load8(audio_emb + tbl + (int64_t)tk[1] * D + d0, e1);
+        load8(audio_emb + 2 * tbl + (int64_t)tk[2] * D + d0, e2);
+        load8(audio_emb + 3 * tbl + (int64_t)tk[3] * D + d0, e3);
+        load8(pe + (int64_t)pos * D + d0, pr);
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            v[i] = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(e0[i], e1[i]), e2[i]), e3[i]), __fmul_rn(alpha_a, pr[i]));
+        store8(x + (int64_t)r * D + d0, v);
+        store8(xb + (int64_t)r * D + d0, v);
+    }
+    float s = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * (1.f / 128.f);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { const float d = v[i] - mean; q += d * d; }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    if (valid && (threadIdx.x & 15) == 0) part[(int64_t)(threadIdx.x >> 4) * part_ld + r] = make_float2(mean, q);
+    ts_end(ts);
+}
+
+// one-time weight preparation for the folded LayerNorm: Wf[n,k] = bf16(gamma_k * W[n,k]), colsum[n] = sum_k Wf[n,k],
+// biasf[n] = bias[n] + sum_k beta_k * W[n,k]   (one warp per output feature)
+__global__ void __launch_bounds__(256) fold_ln_kernel(const bf16* __restrict__ W, int N, int Kd, const float* __restrict__ gamma,
+                                                      const float* __restrict__ beta, const float* __restrict__ bias,
+                                                      bf16* __restrict__ Wf, float* __restrict__ colsum, float* __restrict__ biasf) {
+    const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (n >= N) return;
+    float cs = 0.f, bs = 0.f;
+    for (int k = lane; k < Kd; k += 32) {
+        const float w = __bfloat162float(W[(int64_t)n * Kd + k]);
+        const bf16 wf = __float2bfloat16_rn(w * gamma[k]);
+        Wf[(int64_t)n * Kd + k] = wf;
+        cs += __bfloat162float(wf);
+        bs += beta[k] * w;
+    }
+    cs = warp_sum(cs); bs = warp_sum(bs);
+    if (lane == 0) { colsum[n] = cs; biasf[n] = (bias ? bias[n] : 0.f) + bs; }
+}
+
+int launch_fold_ln(const void* W, int N, int Kd, const float* gamma, const float* beta, const float* bias, void* Wf,
+                   float* colsum, float* biasf, cudaStream_t s) {
+    SSRB_LAUNCH(fold_ln_kernel, cdiv(N, 8), 256, 0, s, reinterpret_cast<const bf16*>(W), N, Kd, gamma, beta, bias,
+                reinterpret_cast<bf16*>(Wf), colsum, biasf);
+    return 0;
+}
+
+int launch_embed_step_fold(const int* next_tok, const UttState* st, int R, int rpu, int K, int D, const float* audio_emb,
+                           int V, const float* pe, float alpha_a, float* x, void* xb, float2* part, int part_ld,
+                           cudaStream_t s) {
+    SSRB_CHECK(K == 4 && D % 128 == 0 && D <= 2048, "embed_step_fold: K must be 4, d_model a multiple of 128 <= 2048");
+    const int threads = ((D / 8) + 31) / 32 * 32;
+    SSRB_LAUNCH_PDL(embed_step_fold_kernel, R, threads, 0, s, next_tok, st, rpu, K, D, audio_emb, V, pe, alpha_a, x,
+                    reinterpret_cast<bf16*>(xb), part, part_ld);
+    return 0;
+}
+
 int launch_embed_prefill(const PosDesc* desc, int M, int D, const float* text_emb, const float* audio_emb, int V,
                          const float* pe, float alpha_t, float alpha_a, float* x, cudaStream_t s) {
     if (M <= 0) return 0;

@@ -38,6 +38,13 @@ int launch_embed_prefill(const PosDesc* desc, int M, int D, const float* text_em
                          const float* pe, float alpha_t, float alpha_a, float* x, cudaStream_t s);
 int launch_embed_step(const int* next_tok, const UttState* st, int R, int rpu, int K, int D, const float* audio_emb,
                       int V, const float* pe, float alpha_a, float* x, cudaStream_t s);
+// decode step with LayerNorm folded into the GEMMs: also writes bf16(x) and the per-128-column {mean, M2} partials
+int launch_embed_step_fold(const int* next_tok, const UttState* st, int R, int rpu, int K, int D, const float* audio_emb,
+                           int V, const float* pe, float alpha_a, float* x, void* xb, float2* part, int part_ld,
+                           cudaStream_t s);
+// Wf = bf16(gamma . W) (row-wise), colsum[n] = sum_k Wf[n,k], biasf[n] = bias[n] + sum_k beta_k W[n,k]
+int launch_fold_ln(const void* W, int N, int Kd, const float* gamma, const float* beta, const float* bias, void* Wf,
+                   float* colsum, float* biasf, cudaStream_t s);
 // y[m] = LN(x[idx ? idx[m] : m]); out dtype SSRB_DTYPE_*
 int launch_layernorm(const float* x, const int* idx, int M, int D, const float* w, const float* b, void* out,
                      int out_dtype, cudaStream_t s);

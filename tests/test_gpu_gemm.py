@@ -86,3 +86,53 @@ def test_tcgen05_bf16(M, N, K, act):
     # run twice: split-K tickets must have been reset and the result must be bit-identical (deterministic reduce)
     again = run_gemm(A, W, b, r, act, _lib.SSRB_DTYPE_BF16, 2)
     assert torch.equal(got, again)
+
+
+LN_SHAPES = [(64, 2048, 2048, 6144), (64, 2048, 8192, 8192), (2, 2048, 2048, 4096), (5, 256, 256, 768), (128, 512, 2048, 2048),
+             (100, 1024, 4096, 4096), (33, 2048, 8192, 6144), (1, 128, 128, 384)]
+
+
+@pytest.mark.parametrize("M,D,K1,N", LN_SHAPES)
+@pytest.mark.parametrize("act", [0, 1, 2])
+def test_tcgen05_folded_layernorm(M, D, K1, N, act):
+    """LayerNorm folded into the decode GEMMs: the residual GEMM emits fp32 x, bf16(x) and per-128-column {mean, M2}
+    partials; the consuming GEMM multiplies bf16(x) by bf16(gamma*W) and applies rstd*(acc - mean*colsum) + (b + W.beta)
+    in its epilogue.  Against (a) torch LayerNorm + linear in fp32 (tolerance 1e-2 x max|C|: operands are bf16) and (b) the same
+    algebra evaluated in fp64 on the rounded operands (tolerance 2e-3: only accumulation order differs).  Rows carry a
+    non-zero mean (1.5 sigma) so the mean*colsum correction is exercised."""
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(M * 31 + N + act)
+    A1 = torch.randn(M, K1, device="cuda", generator=g).bfloat16()
+    W1 = (torch.randn(D, K1, device="cuda", generator=g) / K1 ** 0.5).bfloat16()
+    b1 = torch.randn(D, device="cuda", generator=g)
+    res = torch.randn(M, D, device="cuda", generator=g) + 1.5 * torch.randn(M, 1, device="cuda", generator=g)
+    W2 = (torch.randn(N, D, device="cuda", generator=g) / D ** 0.5).bfloat16()
+    gamma = 1.0 + 0.2 * torch.randn(D, device="cuda", generator=g)
+    beta = 0.2 * torch.randn(D, device="cuda", generator=g)
+    b2 = torch.randn(N, device="cuda", generator=g)
+    X = torch.empty(M, D, dtype=torch.float32, device="cuda")
+    Cout = torch.empty(M, N, dtype=torch.float32, device="cuda")
+
+    def call():
+        _lib.check(lib.ssrb_op_gemm_ln(C.c_void_p(A1.data_ptr()), C.c_void_p(W1.data_ptr()), C.c_void_p(b1.data_ptr()),
+                                       C.c_void_p(res.data_ptr()), C.c_void_p(X.data_ptr()), M, D, K1, C.c_void_p(W2.data_ptr()),
+                                       C.c_void_p(gamma.data_ptr()), C.c_void_p(beta.data_ptr()), C.c_void_p(b2.data_ptr()),
+                                       C.c_void_p(Cout.data_ptr()), N, act, _lib.stream_ptr()), "op_gemm_ln")
+        torch.cuda.synchronize()
+        return X.clone(), Cout.clone()
+
+    x_got, c_got = call()
+    x_want = A1.float() @ W1.float().t() + b1 + res
+    assert (x_got - x_want).abs().max().item() <= 2e-3
+    actf = {0: lambda t: t, 1: torch.relu, 2: torch.nn.functional.gelu}[act]
+    want32 = actf(torch.nn.functional.layer_norm(x_got, (D,), gamma, beta, 1e-5) @ W2.float().t() + b2)
+    tol32 = 1e-2 * max(1.0, want32.abs().max().item())
+    assert (c_got - want32).abs().max().item() <= tol32, ((c_got - want32).abs().max().item(), tol32)
+    xd = x_got.double()
+    mu, var = xd.mean(1, keepdim=True), xd.var(1, unbiased=False, keepdim=True)
+    Wf = (W2.float() * gamma).bfloat16().double()
+    acc = x_got.bfloat16().double() @ Wf.t()
+    want_fold = actf((acc - mu * Wf.sum(1)) / torch.sqrt(var + 1e-5) + b2.double() + W2.double() @ beta.double()).float()
+    assert (c_got - want_fold).abs().max().item() <= 2e-3, (c_got - want_fold).abs().max().item()
+    x2, c2 = call()
+    assert torch.equal(x_got, x2) and torch.equal(c_got, c2)           # fixed-order partial combination: deterministic

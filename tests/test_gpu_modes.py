@@ -35,7 +35,22 @@ out = m.inference_batch(xs, ys, spans, top_k=0, top_p=0.9, stop_repetition=2, cf
 toks = [o[0].cpu().numpy().tolist() for o in out]
 lg = m.last_raw_logits().numpy()
 tf = m.teacher_forced_logits(xs[3], ys[3].T.contiguous()).numpy()
-print("RESULT" + json.dumps({"tokens_sha": hashlib.sha256(json.dumps(toks).encode()).hexdigest(),
+# decode chain vs prefill path on the same tokens (B=1 greedy TTS): logits of the last iteration, incremental vs full forward
+from ssr_speech_b200 import seq
+T, Lx = 30, 8
+x1 = torch.randint(0, 100, (1, Lx), generator=g); y1 = torch.randint(0, 2048, (1, T, 4), generator=g)
+res1 = m.inference(x1.cuda(), torch.tensor([Lx]), x1.cuda(), torch.tensor([Lx]), y1.cuda(), y1.cuda(),
+                   mask_interval=torch.tensor([[[T, T]]]), top_k=1, top_p=1.0, temperature=1.0, stop_repetition=-1, kvcache=1,
+                   aug_text=False)[0]
+raw_last = m.last_raw_logits()[0].numpy()
+r1 = res1[0].cpu().numpy()
+prep = seq.prepare(cfg, y1[0].numpy().T.copy(), [[T, T]])
+gen = seq.delay_pattern(np.concatenate([r1[:, T:], np.full((4, 1), cfg.eog)], 1), cfg.empty_token)
+N = r1.shape[1] - T + 4
+fed = np.concatenate([prep.prompt_tokens, np.full((4, 1), cfg.mts), gen[:, :N - 1]], 1)
+tf1 = m.teacher_forced_logits(x1[0], torch.from_numpy(fed)).numpy()
+inc_err = float(np.abs(tf1[-1] - raw_last).max())
+print("RESULT" + json.dumps({"inc_err": inc_err, "tokens_sha": hashlib.sha256(json.dumps(toks).encode()).hexdigest(),
                              "logits_sha": hashlib.sha256(lg.tobytes()).hexdigest(),
                              "tf_sha": hashlib.sha256(tf.tobytes()).hexdigest(),
                              "tf_probe": tf[::7, :, ::97].tolist(), "n_frames": [len(t[0]) for t in toks]}))
@@ -66,8 +81,11 @@ def test_scheduling_modes_are_bit_identical(base, env):
     assert other["tf_sha"] == base["tf_sha"]
 
 
-@pytest.mark.parametrize("env", [{"SSRB_GEMM_IMPL": "1"}, {"SSRB_ATTN_SIMPLE": "1"}, {"SSRB_PREFILL_SIMT": "1"}])
+@pytest.mark.parametrize("env", [{"SSRB_GEMM_IMPL": "1"}, {"SSRB_ATTN_SIMPLE": "1"}, {"SSRB_PREFILL_SIMT": "1"},
+                                 {"SSRB_LN_FOLD": "0"}])        # separate LayerNorm kernels instead of the folded epilogue
 def test_kernel_variants_agree_within_bf16_tolerance(base, env):
     other = run(env)
     a, b = np.asarray(base["tf_probe"]), np.asarray(other["tf_probe"])
     assert np.abs(a - b).max() <= 2e-2, np.abs(a - b).max()
+    # decode chain (KV cache, folded LayerNorm, swap-AB GEMMs) == prefill path on the same tokens, in every variant
+    assert base["inc_err"] <= 2e-2 and other["inc_err"] <= 2e-2, (base["inc_err"], other["inc_err"])
