@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--codec-chunk", type=int, default=32, help="utterances per codec pass (bounds the activation arena)")
     ap.add_argument("--no-watermark", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-batch-sweep", action="store_true", help="skip the batch 1 / 8 points of BASELINE's metric (reported under other_batches)")
     ap.add_argument("--cpu-iters", type=int, default=12)
     ap.add_argument("--profile-iters", type=int, default=6)
     return ap.parse_args()
@@ -427,6 +428,15 @@ def main():
     except Exception as e:  # pragma: no cover
         breakdown = {"error": repr(e)}
 
+    # ---- the other batch sizes BASELINE.json's metric names (1 and 8 per GPU), same workload, e2e from host buffers -------
+    other = {}
+    if not args.no_batch_sweep and args.batch == 32:
+        for B in (1, 8):
+            try:
+                other[str(B)] = batch_point(B, model, tok, wavs, texts, spans, dc, args, gen_frames, wb, kv_per_pos, S0, n_iter, peak)
+            except Exception as e:  # pragma: no cover
+                other[str(B)] = {"error": repr(e)}
+
     # ---- aggregate over ranks -------------------------------------------------------------------------------------------------
     t = torch.tensor([e2e_ms, dev_ms, dec_ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -470,6 +480,8 @@ def main():
                      "algorithmic_bytes_per_iteration_avg": dec_bytes / (n_iter - 1),
                      "weight_bytes_per_iteration": wb, "iteration_ms_avg": 1e3 * dec_s / (n_iter - 1), "breakdown": breakdown},
     }
+    if other:
+        line["other_batches"] = other
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             cb = cpu_reference_sample(args, args.cpu_iters)
@@ -481,6 +493,34 @@ def main():
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def batch_point(B, model, tok, wavs, texts, spans, dc, args, gen_frames, wb, kv_per_pos, S0, n_iter, peak):
+    """One point of BASELINE's batch sweep on this rank: 1 warm-up + 2 timed passes of the whole hot path (host buffers in,
+    waveforms out) at batch B, with the decode loop's HBM roofline fraction at that batch."""
+    from ssr_speech_b200 import pipeline
+    run = lambda tm: pipeline.inference_batch(model, tok, wavs[:B], texts[:B], spans[:B], dc, cfg_coef=1.5, cfg_stride=5,
+                                              aug_text=True, use_watermark=not args.no_watermark, tts=True, seed=1000, timings=tm)
+    run({})
+    torch.cuda.synchronize()
+    n, acc = 2, {}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        tm = {}
+        run(tm)
+        for k, v in tm.items():
+            acc[k] = acc.get(k, 0.0) + v
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    dec_s = acc.get("lm_decode_ms", 0.0) / n / 1e3
+    R = 2 * B
+    bytes_dec = (n_iter - 1) * wb + sum(R * kv_per_pos * ((S0 + j) + 1) for j in range(1, n_iter))
+    return {"batch_per_gpu": B, "e2e_codec_tokens_per_sec": B * K_CODEBOOKS * gen_frames / (ms / 1e3), "ms_per_step": ms,
+            "e2e_rtf_batch": (ms / 1e3) / (gen_frames / 50.0), "phase_ms_per_step": {k: v / n for k, v in acc.items()},
+            "decode_iteration_ms_avg": 1e3 * dec_s / (n_iter - 1) if dec_s else None,
+            "roofline_frac": bytes_dec / dec_s / 1e9 / peak if dec_s else None}
 
 
 def profile_breakdown(model, lib, texts, ys, spans, dc, args, gen_frames):
