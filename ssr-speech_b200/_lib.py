@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libssr_b200.so")
+LIB_PATH = os.environ.get("SSRB_LIB") or os.path.join(HERE, "libssr_b200.so")     # SSRB_LIB: A/B of two builds (tools/gpu_ab.sh)
 
 SSRB_DTYPE_F32 = 0
 SSRB_DTYPE_BF16 = 1

@@ -136,3 +136,50 @@ def test_tcgen05_folded_layernorm(M, D, K1, N, act):
     assert (c_got - want_fold).abs().max().item() <= 2e-3, (c_got - want_fold).abs().max().item()
     x2, c2 = call()
     assert torch.equal(x_got, x2) and torch.equal(c_got, c2)           # fixed-order partial combination: deterministic
+
+
+def _ln_chain_sha(M, D, K1, N, act):
+    """sha256 of (x, C) of the residual GEMM -> folded-LayerNorm GEMM chain on seeded inputs (used in- and out-of-process)."""
+    import hashlib
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(M * 17 + N + act)
+    A1 = torch.randn(M, K1, device="cuda", generator=g).bfloat16()
+    W1 = (torch.randn(D, K1, device="cuda", generator=g) / K1 ** 0.5).bfloat16()
+    b1 = torch.randn(D, device="cuda", generator=g)
+    res = torch.randn(M, D, device="cuda", generator=g)
+    W2 = (torch.randn(N, D, device="cuda", generator=g) / D ** 0.5).bfloat16()
+    gamma = 1.0 + 0.2 * torch.randn(D, device="cuda", generator=g)
+    beta = 0.2 * torch.randn(D, device="cuda", generator=g)
+    b2 = torch.randn(N, device="cuda", generator=g)
+    X = torch.empty(M, D, dtype=torch.float32, device="cuda")
+    Cout = torch.empty(M, N, dtype=torch.float32, device="cuda")
+    _lib.check(lib.ssrb_op_gemm_ln(C.c_void_p(A1.data_ptr()), C.c_void_p(W1.data_ptr()), C.c_void_p(b1.data_ptr()),
+                                   C.c_void_p(res.data_ptr()), C.c_void_p(X.data_ptr()), M, D, K1, C.c_void_p(W2.data_ptr()),
+                                   C.c_void_p(gamma.data_ptr()), C.c_void_p(beta.data_ptr()), C.c_void_p(b2.data_ptr()),
+                                   C.c_void_p(Cout.data_ptr()), N, act, _lib.stream_ptr()), "op_gemm_ln")
+    torch.cuda.synchronize()
+    return hashlib.sha256(X.cpu().numpy().tobytes() + Cout.cpu().numpy().tobytes()).hexdigest()
+
+
+DEC_CASES = [(64, 2048, 2048, 6144, 0), (64, 2048, 8192, 6144, 0), (2, 2048, 2048, 6144, 0), (16, 2048, 8192, 6144, 0),
+             (33, 2048, 2048, 6144, 0), (128, 2048, 8192, 6144, 0)]
+
+
+def test_dec_role_kernels_bit_identical_to_generic():
+    """The compact per-role decode kernels (gemm_dec_kernel: ROLE_RES for the residual GEMM at 8-way split-K, ROLE_QKV for the
+    folded-LayerNorm consumer at 4-way split-K) keep the generic kernel's arithmetic and summation order: outputs must be
+    bit-identical to a process that runs with SSRB_GEMM_DEC=0 (generic gemm_tc_kernel).  The ReLU/bf16 role (FFN1) is covered
+    by the 830M roll-outs of test_gpu_fullsize.py against the oracle."""
+    import json
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    code = ("import sys, json; sys.path.insert(0, %r); sys.path.insert(0, %r); import test_gpu_gemm as t; "
+            "print('RESULT' + json.dumps([t._ln_chain_sha(*c) for c in t.DEC_CASES]))") % (os.path.dirname(here), here)
+    env = dict(os.environ, SSRB_GEMM_DEC="0")
+    p = subprocess.run([sys.executable, "-c", code], cwd=os.path.dirname(here), env=env, capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr[-2000:]
+    generic = json.loads([l for l in p.stdout.splitlines() if l.startswith("RESULT")][-1][len("RESULT"):])
+    mine = [_ln_chain_sha(*c) for c in DEC_CASES]
+    assert mine == generic

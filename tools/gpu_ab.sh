@@ -1,5 +1,6 @@
 #!/bin/bash
 # A/B of environment switches on the bench workload (no CPU baseline):  tools/gpu_ab.sh name:VAR=val,VAR2=val ...
+# A variant whose list holds TL=1 also dumps its in-kernel timeline.  SSRB_LIB=<path> selects another build of the library.
 # Optional first: PYTEST="tests/test_gpu_modes.py ..." to run tests before; TIMELINE=1 dumps the in-kernel timeline of each variant.
 set -u
 mkdir -p gpurun_out
@@ -8,7 +9,7 @@ if [ -n "${PYTEST:-}" ]; then
   tail -4 gpurun_out/pytest_ab.log
 fi
 run() { name=$1; shift
-  if [ "${TIMELINE:-0}" = "1" ]; then env "$@" timeout 300 python tools/timeline.py --out gpurun_out/tl_$name.npy > gpurun_out/tl_$name.txt 2>&1; tail -1 gpurun_out/tl_$name.txt; fi
+  if [ "${TIMELINE:-0}" = "1" ] || [[ " $* " == *" TL=1 "* ]]; then env "$@" timeout 300 python tools/timeline.py --out gpurun_out/tl_$name.npy > gpurun_out/tl_$name.txt 2>&1; tail -1 gpurun_out/tl_$name.txt; fi
   env "$@" timeout 400 python bench.py --no-cpu-baseline --steps 2 --warmup 3 ${BENCH_ARGS:-} > gpurun_out/ab_$name.json 2> gpurun_out/ab_$name.err; echo "$name rc=$?"; python - <<PY
 import json
 try:
