@@ -19,7 +19,8 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --lo
     python tools/profile_step.py --iters 2 --no-graph > gpurun_out/ncu_launch.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on --nvtx --nvtx-include 'profiled_iterations/' -k regex:attn_decode_tma -s 8 -c 1 -o gpurun_out/attn_decode_full -f \
     python tools/profile_step.py --iters 2 --skip-iters 250 --no-graph > gpurun_out/ncu_attn.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on --nvtx --nvtx-include 'profiled_iterations/' -k regex:gemm_tc -s 4 -c 5 -o gpurun_out/gemm_full -f \
+timeout 600 ncu --set full --clock-control none --import-source on --nvtx --nvtx-include 'profiled_iterations/' -k regex:gemm_ -s 4 -c 5 -o gpurun_out/gemm_full -f \
     python tools/profile_step.py --iters 2 --skip-iters 250 --no-graph > gpurun_out/ncu_gemm.log 2>&1
 fi
-ls -la gpurun_out
+timeout 200 python tools/timeline.py --out gpurun_out/tl_final.npy > gpurun_out/tl_final.txt 2>&1; tail -1 gpurun_out/tl_final.txt
+ls -la gpurun_out | tail -5
