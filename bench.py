@@ -430,7 +430,7 @@ def main():
 
     # ---- the other batch sizes BASELINE.json's metric names (1 and 8 per GPU), same workload, e2e from host buffers -------
     other = {}
-    if not args.no_batch_sweep and args.batch == 32:
+    if not args.no_batch_sweep and args.batch == 32 and world == 1:
         for B in (1, 8):
             try:
                 other[str(B)] = batch_point(B, model, tok, wavs, texts, spans, dc, args, gen_frames, wb, kv_per_pos, S0, n_iter, peak)
