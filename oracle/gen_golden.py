@@ -46,11 +46,21 @@ LM_CASES = [
          kw=dict(top_k=20, top_p=0.9, temperature=0.7, stop_repetition=3, kvcache=1, cfg_coef=1.5, cfg_stride=1, aug_text=True)),
     dict(name="edit_head_nokv", Lx=6, T=24, spans=[[0, 6]], seed=15,
          kw=dict(top_k=1, top_p=1.0, temperature=1.0, stop_repetition=-1, kvcache=0, cfg_coef=1.5, cfg_stride=1, aug_text=False)),
+    # three spans (max_n_spans), the middle one an insertion (empty interval)
+    dict(name="edit3_cfg_sampled", Lx=10, T=44, spans=[[3, 8], [15, 15], [30, 36]], seed=16,
+         kw=dict(top_k=0, top_p=0.9, temperature=1.0, stop_repetition=2, kvcache=1, cfg_coef=1.5, cfg_stride=2, aug_text=True)),
+    # aug_context (ssr.py:564-593): prompt text/codes are prepended, intervals shift by out_len, outputs shift back
+    dict(name="ctx_edit_greedy", Lx=7, T=30, spans=[[10, 18]], seed=17, ctx=dict(Lpx=5, Tp=12),
+         kw=dict(top_k=1, top_p=1.0, temperature=1.0, stop_repetition=-1, kvcache=1, cfg_coef=1.5, cfg_stride=1, aug_text=False,
+                 aug_context=True)),
+    dict(name="ctx_tts_cfg_sampled", Lx=6, T=18, spans=[[18, 18]], seed=18, ctx=dict(Lpx=4, Tp=9),
+         kw=dict(top_k=0, top_p=0.8, temperature=1.0, stop_repetition=2, kvcache=1, cfg_coef=1.5, cfg_stride=2, aug_text=True,
+                 aug_context=True)),
 ]
 SILENCE = [3, 17, 40]   # tiny-vocab stand-ins for the reference default [1388,1898,131]
 
 
-def run_lm_cases():
+def run_lm_cases(only=None):
     ssr = ref_loader.load_reference_ssr()
     cfg = cfg_tiny()
     sd = make_lm_state_dict(cfg, seed=7)
@@ -60,22 +70,33 @@ def run_lm_cases():
     oracle = LMOracle(cfg, sd)
     report = []
     for case in LM_CASES:
+        if only and case["name"] not in only:
+            continue
         g = torch.Generator().manual_seed(case["seed"])
         Lx, T = case["Lx"], case["T"]
         x = torch.randint(0, cfg.text_vocab_size, (1, Lx), generator=g)
         y = torch.randint(0, cfg.audio_vocab_size, (1, T, cfg.n_codebooks), generator=g)
         mi = torch.tensor([case["spans"]], dtype=torch.long)
         kw = dict(case["kw"])
+        ctx = case.get("ctx")
+        if ctx:
+            px = torch.randint(0, cfg.text_vocab_size, (1, ctx["Lpx"]), generator=g)
+            pr = torch.randint(0, cfg.audio_vocab_size, (1, ctx["Tp"], cfg.n_codebooks), generator=g)
+        else:
+            px, pr = x, y
         # ---- reference run (global CPU RNG seeded like inference_v2.seed_everything) -----------
         torch.manual_seed(case["seed"])
         with torch.no_grad():
-            res, marks, masks, nmi = model.inference(x, torch.tensor([Lx]), x, torch.tensor([Lx]), y, y,
+            res, marks, masks, nmi = model.inference(x, torch.tensor([Lx]), px, torch.tensor([px.shape[1]]), y, pr,
                                                      mask_interval=mi, silence_tokens=SILENCE, **kw)
         # ---- oracle run with the same RNG stream ------------------------------------------------
-        prep = seqmod.prepare(cfg, y[0].T.numpy().copy(), case["spans"])
-        okw = {k: v for k, v in kw.items() if k != "kvcache"}
+        use_ctx = bool(kw.get("aug_context")) and sum(b - a for a, b in case["spans"]) < 2 * 50      # ssr.py:564-568
+        xo = torch.cat([px[0], x[0]]) if use_ctx else x[0]                                           # ssr.py:583,592
+        yo = np.concatenate([pr[0].T.numpy(), y[0].T.numpy()], 1) if use_ctx else y[0].T.numpy().copy()
+        prep = seqmod.prepare(cfg, yo, case["spans"], out_len=pr.shape[1] if use_ctx else 0)
+        okw = {k: v for k, v in kw.items() if k not in ("kvcache", "aug_context")}
         torch.manual_seed(case["seed"])
-        spans = oracle.inference(x[0], torch.from_numpy(prep.prompt_tokens), prep.num_spans,
+        spans = oracle.inference(xo, torch.from_numpy(prep.prompt_tokens), prep.num_spans,
                                  silence_tokens=SILENCE, incremental=bool(kw["kvcache"]), **okw)
         ores, omarks, omasks, onmi = seqmod.finalize(cfg, prep, spans)
         same = (ores.shape == tuple(res[0].shape) and np.array_equal(ores, res[0].numpy())
@@ -83,11 +104,11 @@ def run_lm_cases():
                 and onmi == [tuple(m) for m in nmi])
         # ---- the same run again through explicit exponential noise (what the GPU path consumes) --
         torch.manual_seed(case["seed"])
-        uncond = torch.randint(0, cfg.n_text_tokens, (1, Lx))[0] if kw["aug_text"] else None
+        uncond = torch.randint(0, cfg.n_text_tokens, (1, xo.shape[0]))[0] if kw["aug_text"] else None
         n_steps = sum(len(s) for s in spans)
         noise = torch.stack([torch.empty(cfg.n_codebooks, cfg.n_audio_tokens).exponential_(1) for _ in range(n_steps)])
         trace = []
-        spans2 = oracle.inference(x[0], torch.from_numpy(prep.prompt_tokens), prep.num_spans, silence_tokens=SILENCE,
+        spans2 = oracle.inference(xo, torch.from_numpy(prep.prompt_tokens), prep.num_spans, silence_tokens=SILENCE,
                                   uncond_x=uncond, noise=noise, trace=trace, **okw)
         same_noise = all(np.array_equal(a, b) for a, b in zip(spans, spans2))
         report.append((case["name"], same, same_noise, tuple(res.shape)))
@@ -97,6 +118,8 @@ def run_lm_cases():
             x=x[0].numpy(), y=y[0].numpy(), mask_interval=np.asarray(case["spans"]), silence=np.asarray(SILENCE),
             kw=json.dumps(kw), seed=case["seed"], weights_seed=7,
             uncond_x=(uncond.numpy() if uncond is not None else np.zeros(0, np.int64)),
+            prompt_x=(px[0].numpy() if ctx else np.zeros(0, np.int64)),
+            prompt=(pr[0].numpy() if ctx else np.zeros((0, cfg.n_codebooks), np.int64)),
             noise=noise.numpy().astype(np.float32),
             ref_res=res[0].numpy(), ref_marks=marks[0].numpy(), ref_masks=np.asarray(masks), ref_nmi=np.asarray(nmi),
             ref_span_lens=np.asarray([len(s) for s in spans]),
@@ -104,6 +127,8 @@ def run_lm_cases():
             raw_logits_step0=trace[0].raw_logits.numpy(), probs_step0=trace[0].probs.numpy(),
             raw_logits_last=trace[-1].raw_logits.numpy(),
         )
+    if only:
+        return report, None
     # teacher-forced logits fixture straight from the reference modules (no loop)
     g = torch.Generator().manual_seed(99)
     x = torch.randint(0, cfg.text_vocab_size, (11,), generator=g)
@@ -197,7 +222,9 @@ def run_codec_cases():
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(8)
-    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"       # all | lm | codec | lm:<case>,<case> (only those fixtures)
+    if which.startswith("lm:"):
+        run_lm_cases(only=set(which[3:].split(",")))
     if which in ("all", "lm"):
         run_lm_cases()
     if which in ("all", "codec"):

@@ -17,7 +17,8 @@ from ssr_speech_b200.lm import SSR_Speech
 from ssr_speech_b200.synth import make_lm_state_dict
 
 pytestmark = pytest.mark.gpu
-LM_CASES = ["tts_greedy", "edit_cfg_sampled", "edit2_cfg_greedy", "tts_cfg_temp_topk", "edit_head_nokv"]
+LM_CASES = ["tts_greedy", "edit_cfg_sampled", "edit2_cfg_greedy", "tts_cfg_temp_topk", "edit_head_nokv",
+            "edit3_cfg_sampled", "ctx_edit_greedy", "ctx_tts_cfg_sampled"]     # 3 spans; aug_context without / with CFG
 
 
 def make_model(precision, seed=7, cfg=None, **kw):
@@ -42,7 +43,10 @@ def run_case(model, g, noise=True):
     x = torch.from_numpy(g["x"])[None]
     y = torch.from_numpy(g["y"])[None]
     mi = torch.from_numpy(g["mask_interval"])[None]
-    return model.inference(x.cuda(), torch.tensor([x.shape[1]]), x.cuda(), torch.tensor([x.shape[1]]), y.cuda(), y.cuda(),
+    has_ctx = "prompt" in g.files and g["prompt"].shape[0] > 0
+    px = torch.from_numpy(g["prompt_x"])[None] if has_ctx else x
+    pr = torch.from_numpy(g["prompt"])[None] if has_ctx else y
+    return model.inference(x.cuda(), torch.tensor([x.shape[1]]), px.cuda(), torch.tensor([px.shape[1]]), y.cuda(), pr.cuda(),
                            mask_interval=mi, silence_tokens=g["silence"].tolist(),
                            _uncond_x=torch.from_numpy(g["uncond_x"]) if kw["aug_text"] else None,
                            _noise=torch.from_numpy(g["noise"]) if noise else None, **kw)

@@ -13,7 +13,8 @@ from ssr_speech_b200 import seq
 from ssr_speech_b200.config import CodecConfig, cfg_tiny
 from ssr_speech_b200.synth import make_codec_state_dict, make_lm_state_dict
 
-LM_CASES = ["tts_greedy", "edit_cfg_sampled", "edit2_cfg_greedy", "tts_cfg_temp_topk", "edit_head_nokv"]
+LM_CASES = ["tts_greedy", "edit_cfg_sampled", "edit2_cfg_greedy", "tts_cfg_temp_topk", "edit_head_nokv",
+            "edit3_cfg_sampled", "ctx_edit_greedy", "ctx_tts_cfg_sampled"]
 
 
 @pytest.fixture(scope="module")
@@ -28,10 +29,13 @@ def test_lm_oracle_reproduces_reference_tokens(lm_oracle, gold_dir, name):
     g = np.load(os.path.join(gold_dir, f"lm_{name}.npz"))
     kw = json.loads(str(g["kw"]))
     kw.pop("kvcache")
-    prep = seq.prepare(cfg, g["y"].T.copy(), g["mask_interval"].tolist())
+    x, y, out_len = g["x"], g["y"].T.copy(), 0
+    if kw.pop("aug_context", False) and sum(b - a for a, b in g["mask_interval"].tolist()) < 2 * 50:   # ssr.py:564-593
+        x, y, out_len = np.concatenate([g["prompt_x"], x]), np.concatenate([g["prompt"].T, y], 1), g["prompt"].shape[0]
+    prep = seq.prepare(cfg, y, g["mask_interval"].tolist(), out_len=out_len)
     uncond = torch.from_numpy(g["uncond_x"]) if kw["aug_text"] else None
     trace = []
-    spans = oracle.inference(torch.from_numpy(g["x"]), torch.from_numpy(prep.prompt_tokens), prep.num_spans,
+    spans = oracle.inference(torch.from_numpy(x), torch.from_numpy(prep.prompt_tokens), prep.num_spans,
                              silence_tokens=g["silence"].tolist(), uncond_x=uncond, noise=torch.from_numpy(g["noise"]),
                              trace=trace, **kw)
     assert [len(s) for s in spans] == g["ref_span_lens"].tolist()
