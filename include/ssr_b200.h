@@ -215,6 +215,19 @@ int ssrb_op_gemm_ln(const void* A1_dev, const void* W1_dev, const float* bias1_d
                     float* X_out_dev, int M, int D, int K1, const void* W2_dev, const float* gamma_dev,
                     const float* beta_dev, const float* bias2_dev, float* C_out_dev, int N, int act, void* stream);
 
+/* EXPERIMENTAL.  The GEMM chain of one decoder layer between two decode-attention kernels (out-proj + residual, LayerNorm 2,
+ * FFN1 + ReLU, FFN2 + residual, and optionally the NEXT layer's LayerNorm 1 + QKV projection when wqkv != NULL;
+ * transformer.py:321-343,386-388, activation.py:83-89,637) on caller-provided device buffers:
+ *   impl 0 = the four per-GEMM launches the decode chain uses today, impl 1 = the persistent per-layer kernel
+ *   (csrc/gemm_layer.cu, SSRB_LAYER_KERNEL=1 in the engine).  Both must produce the same bits.
+ * ao [M,D] bf16, x_inout [M,D] fp32 (residual stream, updated), weights bf16 [out,in], hid_out [M,F] bf16, qkv_out [M,3D] fp32.
+ * impl 1 needs D % 512 == 0 and F % 512 == 0. */
+int ssrb_op_layer_chain(const void* ao_dev, float* x_inout_dev, const void* wo_dev, const float* bo_dev, const void* w1_dev,
+                        const float* b1_dev, const float* gamma2_dev, const float* beta2_dev, const void* w2_dev,
+                        const float* b2_dev, const void* wqkv_dev, const float* bqkv_dev, const float* gamma1n_dev,
+                        const float* beta1n_dev, void* hid_out_dev, float* qkv_out_dev, int M, int D, int F, int impl,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -86,6 +86,7 @@ struct TsBuf { unsigned long long* buf; unsigned int* idx; unsigned int cap; };
 static __device__ TsBuf g_ts = {nullptr, nullptr, 0};      // one copy per translation unit (no -rdc); armed by ts_arm_tu()
 static inline int ts_arm_tu(const TsBuf& t) { return cudaMemcpyToSymbol(g_ts, &t, sizeof(t)) == cudaSuccess ? 0 : 1; }
 int ts_arm_gemm_tc(const TsBuf& t); int ts_arm_attn_tma(const TsBuf& t); int ts_arm_lm_kernels(const TsBuf& t);
+int ts_arm_gemm_layer(const TsBuf& t);
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -204,5 +205,28 @@ int gemm_simt(const GemmArgs& g, cudaStream_t stream);
 int gemm_tc(const GemmArgs& g, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 size_t gemm_tc_workspace_bytes(int max_rows_decode, int max_n);
 bool gemm_tc_supported(const GemmArgs& g);
+
+// ---- persistent per-layer decode GEMM chain (gemm_layer.cu; experimental, SSRB_LAYER_KERNEL=1) ---------------------------
+// One launch runs the GEMMs between two attention kernels of a decode iteration with the LayerNorms folded exactly as the
+// per-GEMM chain does (run_layer_fold in lm_engine.cu):
+//   phase 0  x += ao . Wo^T + bo                      (writes fp32 x, bf16(x) -> hn, row statistics -> ln_part)
+//   phase 1  hid = relu(LN2(x) . W1^T + b1)           (bf16)
+//   phase 2  x += hid . W2^T + b2                     (writes x, hn, ln_part)
+//   phase 3  qkv = LN1'(x) . Wqkv'^T + bqkv'          (fp32; the NEXT layer's projection; skipped when wqkv_next == null)
+struct LayerChainArgs {
+    int M = 0, D = 0, F = 0;                            // rows (<= 128), d_model, ffn width
+    const void* ao = nullptr;                           // bf16 [M, D] attention output
+    float* x = nullptr;                                 // fp32 [M, D] residual stream (in / out)
+    void* hn = nullptr;                                 // bf16 [M, D]
+    void* hid = nullptr;                                // bf16 [M, F]
+    float* qkv = nullptr;                               // fp32 [M, 3D]
+    float2* ln_part = nullptr; int part_ld = 0;         // [D / 128][part_ld] {mean, M2}
+    float ln_eps = 1e-5f;
+    const void *wo = nullptr, *w1f = nullptr, *w2 = nullptr, *wqkv_next = nullptr;     // bf16, LayerNorm gamma folded (w1f, wqkv_next)
+    const float *bo = nullptr, *b1f = nullptr, *c1 = nullptr, *b2 = nullptr, *bqkv_next = nullptr, *cqkv_next = nullptr;
+    unsigned int* gbar = nullptr;                       // 64 zero-initialised words: grid barrier {count @0, generation @32}
+};
+bool gemm_layer_supported(int M, int D, int F);         // shape + co-residency of the persistent grid on this device
+int gemm_layer(const LayerChainArgs& a, cudaStream_t stream);
 
 }  // namespace ssrb

@@ -29,6 +29,12 @@ static bool ln_fold_enabled() {
     static const bool on = [] { const char* e = getenv("SSRB_LN_FOLD"); return !(e && e[0] == '0'); }();
     return on;
 }
+// SSRB_LAYER_KERNEL=1 (experimental, default off): out-proj -> FFN1 -> FFN2 -> next QKV as ONE persistent launch per layer
+// (gemm_layer.cu) instead of four
+static bool layer_kernel_enabled() {
+    static const bool on = [] { const char* e = getenv("SSRB_LAYER_KERNEL"); return e && e[0] == '1'; }();
+    return on;
+}
 static bool attn_prefetch_enabled() {
     static const bool on = [] { const char* e = getenv("SSRB_ATTN_PREFETCH"); return !(e && e[0] == '0'); }();
     return on;
@@ -71,6 +77,8 @@ struct ssrb_lm {
     bool fold_ok = false;      // the configuration supports the folded chain (bf16 tensor-core GEMMs, d_model <= 2048)
     bool fold_dirty = true;    // weights changed since the folded copies were built
     bool fold = false;         // the open batch decodes through the folded chain (R <= 128)
+    bool layer_kernel = false; // ... with the persistent per-layer GEMM kernel (gemm_layer.cu)
+    unsigned int* gbar = nullptr;   // its grid barrier {count, generation}
     float2* ln_part = nullptr; // [max_rows][d_model / 128] {mean, M2} partials of the residual stream
     std::map<std::string, bool> loaded;
     // workspace
@@ -186,6 +194,8 @@ int ssrb_lm_create(const ssrb_lm_config* c, int device, ssrb_lm** out) {
     SSRB_TRY(dev_alloc((void**)&lm->d_seq_len, R * 4)); SSRB_TRY(dev_alloc((void**)&lm->d_next_tok, R * K * 4));
     SSRB_TRY(dev_alloc((void**)&lm->d_gen_tok, (size_t)R * c->max_steps * K * 4));
     SSRB_TRY(dev_alloc((void**)&lm->d_iter, 4));
+    SSRB_TRY(dev_alloc((void**)&lm->gbar, 64 * 4));
+    SSRB_CUDA(cudaMemset(lm->gbar, 0, 64 * 4));
     *out = lm;
     return 0;
 }
@@ -204,7 +214,7 @@ void ssrb_lm_destroy(ssrb_lm* lm) {
                   lm->qkv, lm->logits, lm->hn, lm->ao, lm->hid, lm->hlast, lm->hh, lm->kcache, lm->vcache, lm->attn_ws,
                   lm->tickets, lm->tc_ws, lm->d_desc, lm->d_rows, lm->d_slots, lm->d_row_ids, lm->d_row_start,
                   lm->d_row_len, lm->d_last_idx, lm->d_state, lm->d_seq_len, lm->d_next_tok, lm->d_gen_tok, lm->d_iter,
-                  lm->staging, lm->hw1_f, lm->hc1, lm->hb1_f, lm->ln_part};
+                  lm->staging, lm->hw1_f, lm->hc1, lm->hb1_f, lm->ln_part, lm->gbar};
     for (void* p : ps) cudaFree(p);
     delete lm;
 }
@@ -371,23 +381,31 @@ static int run_layer(ssrb_lm* lm, int n, int M, bool prefill, int n_rows, int ma
 
 // one decoder layer of a decode iteration with both LayerNorms folded into the GEMMs that consume them (gemm_tc.cu):
 // hn holds bf16(x), ln_part the row statistics of x; the two residual GEMMs refresh both while they write x.
-static int run_layer_fold(ssrb_lm* lm, int n, int M, cudaStream_t s) {
-    const int D = lm->D, F = lm->F, H = lm->H;
+static int fold_qkv(ssrb_lm* lm, int n, int M, cudaStream_t s) {
+    const int D = lm->D;
     const LayerW& w = lm->layers[n];
-    const size_t e = lm->esz;
-    void* kc = (char*)lm->kcache + (size_t)n * lm->kv_layer_elems * e;
-    void* vc = (char*)lm->vcache + (size_t)n * lm->kv_layer_elems * e;
     GemmArgs g;
     g.A = lm->hn; g.lda = D; g.W = w.wqkv_f; g.ldw = D; g.bias = w.bqkv_f; g.C = lm->qkv; g.ldc = 3 * D;
     g.M = M; g.N = 3 * D; g.K = D; g.c_dtype = SSRB_DTYPE_F32;
     g.ln_part = lm->ln_part; g.part_ld = lm->cfg.max_rows; g.ln_blocks = D / 128; g.ln_colsum = w.cqkv;
-    SSRB_TRY(gemm(lm, g, s));
-    {
-        ProfScope ps(lm, PC_ATTN, s);
-        SSRB_TRY(launch_attn_decode(lm->qkv, M, D, H, kc, vc, lm->wdt, lm->cfg.max_seq, lm->d_seq_len, lm->d_state,
-                                    lm->rpu, lm->attn_ws, lm->tickets, lm->ao, lm->wdt, attn_prefetch_enabled() ? 1 : 0, s));
-    }
-    g = GemmArgs();
+    return gemm(lm, g, s);
+}
+
+static int fold_attn(ssrb_lm* lm, int n, int M, cudaStream_t s) {
+    const size_t e = lm->esz;
+    void* kc = (char*)lm->kcache + (size_t)n * lm->kv_layer_elems * e;
+    void* vc = (char*)lm->vcache + (size_t)n * lm->kv_layer_elems * e;
+    ProfScope ps(lm, PC_ATTN, s);
+    return launch_attn_decode(lm->qkv, M, lm->D, lm->H, kc, vc, lm->wdt, lm->cfg.max_seq, lm->d_seq_len, lm->d_state,
+                              lm->rpu, lm->attn_ws, lm->tickets, lm->ao, lm->wdt, attn_prefetch_enabled() ? 1 : 0, s);
+}
+
+static int run_layer_fold(ssrb_lm* lm, int n, int M, cudaStream_t s) {
+    const int D = lm->D, F = lm->F;
+    const LayerW& w = lm->layers[n];
+    SSRB_TRY(fold_qkv(lm, n, M, s));
+    SSRB_TRY(fold_attn(lm, n, M, s));
+    GemmArgs g;
     g.A = lm->ao; g.lda = D; g.W = w.wo; g.ldw = D; g.bias = w.bo; g.residual = lm->x; g.ldr = D; g.C = lm->x; g.ldc = D;
     g.M = M; g.N = D; g.K = D; g.c_dtype = SSRB_DTYPE_F32;
     g.C2 = lm->hn; g.ldc2 = D; g.part_out = lm->ln_part; g.part_ld = lm->cfg.max_rows;
@@ -403,6 +421,25 @@ static int run_layer_fold(ssrb_lm* lm, int n, int M, cudaStream_t s) {
     g.C2 = lm->hn; g.ldc2 = D; g.part_out = lm->ln_part; g.part_ld = lm->cfg.max_rows;
     SSRB_TRY(gemm(lm, g, s));
     return 0;
+}
+
+// the same layer with its four GEMM launches replaced by one persistent launch (gemm_layer.cu, SSRB_LAYER_KERNEL=1): layer n's
+// attention, then out-proj -> FFN1 -> FFN2 -> layer n+1's QKV projection (layer 0's projection is launched by the caller)
+static int run_layer_persistent(ssrb_lm* lm, int n, int M, cudaStream_t s) {
+    const LayerW& w = lm->layers[n];
+    SSRB_TRY(fold_attn(lm, n, M, s));
+    ProfScope ps(lm, PC_GEMM, s);
+    LayerChainArgs a;
+    a.M = M; a.D = lm->D; a.F = lm->F;
+    a.ao = lm->ao; a.x = lm->x; a.hn = lm->hn; a.hid = lm->hid; a.qkv = lm->qkv;
+    a.ln_part = lm->ln_part; a.part_ld = lm->cfg.max_rows;
+    a.wo = w.wo; a.bo = w.bo; a.w1f = w.w1_f; a.b1f = w.b1_f; a.c1 = w.c1; a.w2 = w.w2; a.b2 = w.b2;
+    if (n + 1 < lm->L) {
+        const LayerW& nx = lm->layers[n + 1];
+        a.wqkv_next = nx.wqkv_f; a.bqkv_next = nx.bqkv_f; a.cqkv_next = nx.cqkv;
+    }
+    a.gbar = lm->gbar;
+    return gemm_layer(a, s);
 }
 
 // final LN (gathered rows) + 4 prediction heads -> logits [M, K, V] fp32
@@ -426,7 +463,12 @@ static int enqueue_step(ssrb_lm* lm, cudaStream_t s) {
         { ProfScope ps(lm, PC_SMALL, s);
           SSRB_TRY(launch_embed_step_fold(lm->d_next_tok, lm->d_state, lm->R, lm->rpu, lm->K, lm->D, lm->audio_emb, lm->V,
                                           lm->pe, lm->alpha_a, lm->x, lm->hn, lm->ln_part, lm->cfg.max_rows, s)); }
-        for (int n = 0; n < lm->L; n++) SSRB_TRY(run_layer_fold(lm, n, lm->R, s));
+        if (lm->layer_kernel) {
+            SSRB_TRY(fold_qkv(lm, 0, lm->R, s));
+            for (int n = 0; n < lm->L; n++) SSRB_TRY(run_layer_persistent(lm, n, lm->R, s));
+        } else {
+            for (int n = 0; n < lm->L; n++) SSRB_TRY(run_layer_fold(lm, n, lm->R, s));
+        }
         // final LayerNorm folded into the first head layer
         const int D = lm->D, K = lm->K, V = lm->V, Hh = lm->Hh;
         GemmArgs g;
@@ -518,6 +560,7 @@ int ssrb_lm_begin(ssrb_lm* lm, const ssrb_lm_batch* b, const ssrb_sampling* sp, 
     lm->n_utt = U; lm->rpu = rpu; lm->R = R; lm->noise = noise_dev;
     SSRB_TRY(fold_weights(lm, s));
     lm->fold = lm->fold_ok && R <= 128;
+    lm->layer_kernel = lm->fold && layer_kernel_enabled() && gemm_layer_supported(R, lm->D, lm->F);
     if (lm->graph) { cudaGraphExecDestroy(lm->graph); lm->graph = nullptr; }
     SampleParams& p = lm->sp;
     p.K = K; p.V = lm->V; p.rpu = rpu; p.empty_token = lm->cfg.empty_token; p.eog = lm->cfg.eog; p.eos = lm->cfg.eos;
@@ -782,7 +825,7 @@ int ssrb_lm_profile_steps(ssrb_lm* lm, int n_steps, void* stream, double* ms_by_
 
 int ssrb_debug_timeline(unsigned long long* dev_buf, unsigned int* dev_idx, unsigned int cap) {
     TsBuf t{dev_buf, dev_idx, cap};
-    SSRB_CHECK(!ts_arm_gemm_tc(t) && !ts_arm_attn_tma(t) && !ts_arm_lm_kernels(t), "cudaMemcpyToSymbol failed");
+    SSRB_CHECK(!ts_arm_gemm_tc(t) && !ts_arm_attn_tma(t) && !ts_arm_lm_kernels(t) && !ts_arm_gemm_layer(t), "cudaMemcpyToSymbol failed");
     return 0;
 }
 
@@ -823,6 +866,68 @@ int ssrb_op_gemm_ln(const void* A1, const void* W1, const float* bias1, const fl
     if (!rc) rc = gemm_tc_supported(g) ? gemm_tc(g, nullptr, 0, s) : 1;
     cudaError_t ce = cudaStreamSynchronize(s);
     cudaFree(xb); cudaFree(w2f); cudaFree(cs); cudaFree(bf); cudaFree(part);
+    if (rc) return rc;
+    SSRB_CUDA(ce);
+    return 0;
+}
+
+// One layer's GEMM chain between two attention kernels, on caller-provided buffers: impl 0 = the four per-GEMM launches of
+// run_layer_fold, impl 1 = the persistent layer kernel (gemm_layer.cu).  Same folded weights, same buffers, same outputs.
+int ssrb_op_layer_chain(const void* ao, float* x_inout, const void* wo, const float* bo, const void* w1, const float* b1,
+                        const float* gamma2, const float* beta2, const void* w2, const float* b2, const void* wqkv,
+                        const float* bqkv, const float* gamma1n, const float* beta1n, void* hid_out, float* qkv_out, int M,
+                        int D, int F, int impl, void* stream) {
+    SSRB_CHECK(ao && x_inout && wo && bo && w1 && b1 && gamma2 && beta2 && w2 && b2 && hid_out, "null argument");
+    SSRB_CHECK(!wqkv || (bqkv && gamma1n && beta1n && qkv_out), "the QKV phase needs bias, LayerNorm parameters and an output");
+    SSRB_CHECK(M >= 1 && M <= 128 && D % 128 == 0 && D <= 2048 && F % 128 == 0, "op_layer_chain: M <= 128, d_model % 128 == 0 <= 2048");
+    cudaStream_t s = (cudaStream_t)stream;
+    void *hn = nullptr, *w1f = nullptr, *wqf = nullptr; float *c1 = nullptr, *b1f = nullptr, *cq = nullptr, *bqf = nullptr;
+    float2* part = nullptr; unsigned int* gbar = nullptr;
+    SSRB_CUDA(cudaMalloc(&hn, (size_t)M * D * 2)); SSRB_CUDA(cudaMalloc(&w1f, (size_t)F * D * 2));
+    SSRB_CUDA(cudaMalloc((void**)&c1, (size_t)F * 4)); SSRB_CUDA(cudaMalloc((void**)&b1f, (size_t)F * 4));
+    SSRB_CUDA(cudaMalloc((void**)&part, (size_t)M * (D / 128) * sizeof(float2)));
+    SSRB_CUDA(cudaMalloc((void**)&gbar, 64 * 4)); SSRB_CUDA(cudaMemsetAsync(gbar, 0, 64 * 4, s));
+    int rc = launch_fold_ln(w1, F, D, gamma2, beta2, b1, w1f, c1, b1f, s);
+    if (wqkv) {
+        SSRB_CUDA(cudaMalloc(&wqf, (size_t)3 * D * D * 2));
+        SSRB_CUDA(cudaMalloc((void**)&cq, (size_t)3 * D * 4)); SSRB_CUDA(cudaMalloc((void**)&bqf, (size_t)3 * D * 4));
+        if (!rc) rc = launch_fold_ln(wqkv, 3 * D, D, gamma1n, beta1n, bqkv, wqf, cq, bqf, s);
+    }
+    if (!rc && impl == 1) {
+        if (!gemm_layer_supported(M, D, F)) { set_error("op_layer_chain: the persistent layer kernel does not support this shape / device"); rc = 1; }
+        LayerChainArgs a;
+        a.M = M; a.D = D; a.F = F; a.ao = ao; a.x = x_inout; a.hn = hn; a.hid = hid_out; a.qkv = qkv_out;
+        a.ln_part = part; a.part_ld = M;
+        a.wo = wo; a.bo = bo; a.w1f = w1f; a.b1f = b1f; a.c1 = c1; a.w2 = w2; a.b2 = b2;
+        if (wqkv) { a.wqkv_next = wqf; a.bqkv_next = bqf; a.cqkv_next = cq; }
+        a.gbar = gbar;
+        if (!rc) rc = gemm_layer(a, s);
+    } else if (!rc) {
+        GemmArgs g;
+        g.A = ao; g.lda = D; g.W = wo; g.ldw = D; g.bias = bo; g.residual = x_inout; g.ldr = D; g.C = x_inout; g.ldc = D;
+        g.M = M; g.N = D; g.K = D; g.ab_dtype = SSRB_DTYPE_BF16; g.c_dtype = SSRB_DTYPE_F32;
+        g.C2 = hn; g.ldc2 = D; g.part_out = part; g.part_ld = M;
+        rc = gemm_tc_supported(g) ? gemm_tc(g, nullptr, 0, s) : 1;
+        g = GemmArgs();
+        g.A = hn; g.lda = D; g.W = w1f; g.ldw = D; g.bias = b1f; g.C = hid_out; g.ldc = F;
+        g.M = M; g.N = F; g.K = D; g.act = ACT_RELU; g.ab_dtype = SSRB_DTYPE_BF16; g.c_dtype = SSRB_DTYPE_BF16;
+        g.ln_part = part; g.part_ld = M; g.ln_blocks = D / 128; g.ln_colsum = c1;
+        if (!rc) rc = gemm_tc_supported(g) ? gemm_tc(g, nullptr, 0, s) : 1;
+        g = GemmArgs();
+        g.A = hid_out; g.lda = F; g.W = w2; g.ldw = F; g.bias = b2; g.residual = x_inout; g.ldr = D; g.C = x_inout; g.ldc = D;
+        g.M = M; g.N = D; g.K = F; g.ab_dtype = SSRB_DTYPE_BF16; g.c_dtype = SSRB_DTYPE_F32;
+        g.C2 = hn; g.ldc2 = D; g.part_out = part; g.part_ld = M;
+        if (!rc) rc = gemm_tc_supported(g) ? gemm_tc(g, nullptr, 0, s) : 1;
+        if (wqkv) {
+            g = GemmArgs();
+            g.A = hn; g.lda = D; g.W = wqf; g.ldw = D; g.bias = bqf; g.C = qkv_out; g.ldc = 3 * D;
+            g.M = M; g.N = 3 * D; g.K = D; g.ab_dtype = SSRB_DTYPE_BF16; g.c_dtype = SSRB_DTYPE_F32;
+            g.ln_part = part; g.part_ld = M; g.ln_blocks = D / 128; g.ln_colsum = cq;
+            if (!rc) rc = gemm_tc_supported(g) ? gemm_tc(g, nullptr, 0, s) : 1;
+        }
+    }
+    cudaError_t ce = cudaStreamSynchronize(s);
+    cudaFree(hn); cudaFree(w1f); cudaFree(wqf); cudaFree(c1); cudaFree(b1f); cudaFree(cq); cudaFree(bqf); cudaFree(part); cudaFree(gbar);
     if (rc) return rc;
     SSRB_CUDA(ce);
     return 0;

@@ -53,7 +53,7 @@ inc_err = float(np.abs(tf1[-1] - raw_last).max())
 print("RESULT" + json.dumps({"inc_err": inc_err, "tokens_sha": hashlib.sha256(json.dumps(toks).encode()).hexdigest(),
                              "logits_sha": hashlib.sha256(lg.tobytes()).hexdigest(),
                              "tf_sha": hashlib.sha256(tf.tobytes()).hexdigest(),
-                             "tf_probe": tf[::7, :, ::97].tolist(), "n_frames": [len(t[0]) for t in toks]}))
+                             "tf_probe": tf[::7, :, ::97].tolist(), "lg_probe": lg[:, :, ::97].tolist(), "n_frames": [len(t[0]) for t in toks]}))
 """
 
 
