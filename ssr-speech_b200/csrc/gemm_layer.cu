@@ -232,7 +232,10 @@ __device__ __forceinline__ void epi_phase(const LayerPrm& prm, const int p, EpiC
         if (lane == 0) mbar_arrive_local(e.tempty0 + 8u * buf);      // 4 arrivals free the accumulator for the MMA thread
         smem_release_cluster();
         epi_bar();
-        if (e.warp == 2 && lane < S) peer_arrive(parked, (uint32_t)(geo.gbase + lane));
+        if (e.warp == 2) {
+            smem_release_cluster();                          // cumulative over the other warps' stores (ordered by the barrier)
+            if (lane < S) peer_arrive(parked, (uint32_t)(geo.gbase + lane));
+        }
         mbar_wait_acquire_cluster(parked, (uint32_t)(nmode & 1));    // every peer's partial tile is parked and visible
 
         // ---- reduce-scatter through distributed shared memory: rows s, s+S, ...; 512 B of one peer per warp request ----

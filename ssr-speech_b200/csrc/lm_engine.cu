@@ -561,6 +561,7 @@ int ssrb_lm_begin(ssrb_lm* lm, const ssrb_lm_batch* b, const ssrb_sampling* sp, 
     SSRB_TRY(fold_weights(lm, s));
     lm->fold = lm->fold_ok && R <= 128;
     lm->layer_kernel = lm->fold && layer_kernel_enabled() && gemm_layer_supported(R, lm->D, lm->F);
+    if (lm->layer_kernel) SSRB_CUDA(cudaMemsetAsync(lm->gbar, 0, 64 * 4, s));   // a launch that died mid-barrier must not poison the next batch
     if (lm->graph) { cudaGraphExecDestroy(lm->graph); lm->graph = nullptr; }
     SampleParams& p = lm->sp;
     p.K = K; p.V = lm->V; p.rpu = rpu; p.empty_token = lm->cfg.empty_token; p.eog = lm->cfg.eog; p.eos = lm->cfg.eos;
