@@ -56,6 +56,14 @@ LM_CASES = [
     dict(name="ctx_tts_cfg_sampled", Lx=6, T=18, spans=[[18, 18]], seed=18, ctx=dict(Lpx=4, Tp=9),
          kw=dict(top_k=0, top_p=0.8, temperature=1.0, stop_repetition=2, kvcache=1, cfg_coef=1.5, cfg_stride=2, aug_text=True,
                  aug_context=True)),
+    # stop_repetition penalty (ssr.py:727-736): the greedy roll-outs of these seeds sit on tokens 34 / 25 for tens of steps, so with
+    # those ids as "silence" tokens the consecutive-repeat counter exceeds stop_repetition and the logit is rescaled
+    dict(name="tts_rep_greedy", Lx=12, T=20, spans=[[20, 20]], seed=26, silence=[25, 34, 37],
+         kw=dict(top_k=1, top_p=1.0, temperature=1.0, stop_repetition=1, kvcache=1, cfg_coef=1.5, cfg_stride=1, aug_text=False)),
+    dict(name="tts_rep_cfg_lowtemp", Lx=12, T=20, spans=[[20, 20]], seed=26, silence=[25, 34, 37, 42],
+         kw=dict(top_k=3, top_p=1.0, temperature=0.3, stop_repetition=1, kvcache=1, cfg_coef=1.5, cfg_stride=2, aug_text=True)),
+    dict(name="tts_rep_cfg_greedy", Lx=12, T=20, spans=[[20, 20]], seed=27, silence=[25, 34, 37, 42],
+         kw=dict(top_k=1, top_p=1.0, temperature=1.0, stop_repetition=2, kvcache=1, cfg_coef=1.5, cfg_stride=1, aug_text=True)),
 ]
 SILENCE = [3, 17, 40]   # tiny-vocab stand-ins for the reference default [1388,1898,131]
 
@@ -78,6 +86,7 @@ def run_lm_cases(only=None):
         y = torch.randint(0, cfg.audio_vocab_size, (1, T, cfg.n_codebooks), generator=g)
         mi = torch.tensor([case["spans"]], dtype=torch.long)
         kw = dict(case["kw"])
+        SILENCE = case.get("silence", globals()["SILENCE"])
         ctx = case.get("ctx")
         if ctx:
             px = torch.randint(0, cfg.text_vocab_size, (1, ctx["Lpx"]), generator=g)

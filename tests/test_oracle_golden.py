@@ -14,7 +14,8 @@ from ssr_speech_b200.config import CodecConfig, cfg_tiny
 from ssr_speech_b200.synth import make_codec_state_dict, make_lm_state_dict
 
 LM_CASES = ["tts_greedy", "edit_cfg_sampled", "edit2_cfg_greedy", "tts_cfg_temp_topk", "edit_head_nokv",
-            "edit3_cfg_sampled", "ctx_edit_greedy", "ctx_tts_cfg_sampled"]
+            "edit3_cfg_sampled", "ctx_edit_greedy", "ctx_tts_cfg_sampled",
+            "tts_rep_greedy", "tts_rep_cfg_lowtemp", "tts_rep_cfg_greedy"]      # stop_repetition penalty fires (ssr.py:727-736)
 
 
 @pytest.fixture(scope="module")
@@ -101,3 +102,14 @@ def test_codec_oracle_demo_wav_roundtrip(gold_dir):
     np.testing.assert_allclose(emb.numpy(), g["ref_emb"], atol=1e-6)
     assert np.array_equal(codes.numpy(), g["ref_codes"])
     np.testing.assert_allclose(o.decode(codes).numpy(), g["ref_dec"], atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["tts_rep_greedy", "tts_rep_cfg_lowtemp", "tts_rep_cfg_greedy"])
+def test_repetition_fixtures_exercise_the_penalty_branch(gold_dir, name):
+    """ssr.py:727-736 only acts when a silence token repeats more than stop_repetition times: check on the reference's own
+    tokens that these fixtures reach it (the other fixtures never do), so parity on them covers the branch."""
+    from test_gpu_z_repetition import penalty_steps
+    g = np.load(os.path.join(gold_dir, f"lm_{name}.npz"))
+    assert penalty_steps(g, cfg_tiny().eog) >= 1
+    for other in ("tts_greedy", "edit_cfg_sampled", "tts_cfg_temp_topk"):
+        assert penalty_steps(np.load(os.path.join(gold_dir, f"lm_{other}.npz")), cfg_tiny().eog) == 0
