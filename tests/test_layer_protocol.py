@@ -1,0 +1,49 @@
+"""Host-side check of the synchronisation protocol of the experimental persistent layer kernel (csrc/gemm_layer.cu): the
+discrete-event model in tools/layer_protocol_sim.py mirrors the kernel's producer / MMA / epilogue control flow, mbarrier
+parities, remote arrives and grid barrier, and is run under random schedules.  No GPU involved."""
+import importlib.util
+import os
+import random
+
+import pytest
+
+from conftest import ROOT
+
+
+def _sim():
+    spec = importlib.util.spec_from_file_location("layer_protocol_sim", os.path.join(ROOT, "tools", "layer_protocol_sim.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_protocol_terminates_and_reads_the_right_tiles():
+    assert _sim().check(seeds=8, big=False) == 32
+
+
+def test_work_decomposition_covers_every_tile_slice_once():
+    geo = _sim().geo
+    for D, F, ncl in [(2048, 8192, 16), (512, 2048, 16), (1536, 6144, 11), (1024, 4096, 8)]:
+        n_tiles = [D // 128, F // 128, D // 128, 3 * D // 128]
+        for p in range(4):
+            S = 4 if p & 1 else 8
+            seen = set()
+            for c in range(ncl):
+                for r in range(8):
+                    _, _, s, n_act, tpr, off = geo(p, ncl, n_tiles[p], c, r)
+                    for a in range(n_act):
+                        key = (a * tpr + off, s)
+                        assert key not in seen and key[0] < n_tiles[p]
+                        seen.add(key)
+            assert len(seen) == n_tiles[p] * S
+
+
+def test_model_detects_a_missing_wait():
+    """The model is only worth something if it fails on a broken protocol: drop the wait that protects the park buffer."""
+    src = open(os.path.join(ROOT, "tools", "layer_protocol_sim.py")).read()
+    broken = src.replace("                    yield lambda bar=bar, par=par: bar.passed(par)\n                    pend = None", "                    pend = None")
+    assert broken != src
+    ns = {"__name__": "broken_sim"}
+    exec(compile(broken, "broken_sim", "exec"), ns)
+    with pytest.raises(AssertionError):
+        ns["check"](seeds=6, big=False)
