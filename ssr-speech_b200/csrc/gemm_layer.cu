@@ -66,6 +66,26 @@ template <int QROWS> struct LayerCfg {
 __device__ __forceinline__ void mbar_arrive_local(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// Every spin in this kernel is bounded: a protocol bug would otherwise hang the GPU until the box is reclaimed.  After
+// LK_WATCHDOG_NS of waiting the thread traps; the launch fails with an error instead of never finishing.
+#ifndef LK_WATCHDOG_NS
+#define LK_WATCHDOG_NS 2000000000ull
+#endif
+__device__ __forceinline__ void spin_guard(unsigned long long& t0) {
+    const unsigned long long now = globaltimer_ns();
+    if (t0 == 0) t0 = now;
+    else if (now - t0 > LK_WATCHDOG_NS) __trap();
+}
+__device__ __forceinline__ void lk_wait(uint32_t bar, uint32_t parity) {       // mbar_wait of tc_ptx.cuh with the watchdog
+    uint32_t ok;
+    unsigned long long t0 = 0;
+    for (;;) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) break;
+        spin_guard(t0);
+    }
+}
 // Cluster-level signalling between the epilogue warps of peer CTAs.  Default: fence-fence synchronisation — a release fence
 // restricted to this CTA's shared memory (MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC.S in SASS, no GPU-scope membar on the per-tile
 // critical path), relaxed remote arrive, relaxed wait, acquire fence restricted to shared::cluster.  LK_STRONG_SYNC=1 uses
@@ -102,26 +122,32 @@ __device__ __forceinline__ void peer_arrive_relaxed(uint32_t local_bar, uint32_t
 // wait, then acquire the peers' shared-memory writes (before ld.shared::cluster)
 __device__ __forceinline__ void mbar_wait_acquire_cluster(uint32_t bar, uint32_t parity) {
     uint32_t ok;
+    unsigned long long t0 = 0;
+    for (;;) {
 #if LK_STRONG_SYNC
-    do {
         asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
                      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    } while (!ok);
 #else
-    do {
         asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.relaxed.cluster.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
                      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    } while (!ok);
+#endif
+        if (ok) break;
+        spin_guard(t0);
+    }
+#if !LK_STRONG_SYNC
     asm volatile("fence.acquire.sync_restrict::shared::cluster.cluster;" ::: "memory");
 #endif
 }
 // wait only (write-after-read protection of the park buffer: nothing to acquire)
 __device__ __forceinline__ void mbar_wait_relaxed_cluster(uint32_t bar, uint32_t parity) {
     uint32_t ok;
-    do {
+    unsigned long long t0 = 0;
+    for (;;) {
         asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.relaxed.cluster.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
                      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    } while (!ok);
+        if (ok) break;
+        spin_guard(t0);
+    }
 }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }      // the 4 epilogue warps
 
@@ -131,7 +157,7 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-// one thread per CTA, after the CTA's writers executed __threadfence() and a CTA-level barrier
+// one thread per CTA, after a CTA-level barrier behind the CTA's writers and a __threadfence() of its own
 __device__ __forceinline__ void grid_arrive(unsigned int* gbar, unsigned int n_cta) {
     unsigned int old;
     asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(gbar) : "memory");
@@ -141,7 +167,11 @@ __device__ __forceinline__ void grid_arrive(unsigned int* gbar, unsigned int n_c
     }
 }
 __device__ __forceinline__ void grid_wait(const unsigned int* gbar, unsigned int target) {
-    while ((int)(ld_acquire_gpu(gbar + 32) - target) < 0) __nanosleep(32);
+    unsigned long long t0 = 0;
+    while ((int)(ld_acquire_gpu(gbar + 32) - target) < 0) {
+        __nanosleep(32);
+        spin_guard(t0);
+    }
 }
 
 // split-K geometry of a phase inside the 8-CTA cluster: S slices per tile, 8 / S tiles side by side
@@ -210,7 +240,7 @@ __device__ __forceinline__ void epi_phase(const LayerPrm& prm, const int p, EpiC
     for (int a = 0; a < geo.n_act; a++) {
         const int tile = a * geo.tpr + geo.off;
         const int buf = e.j & 1;
-        mbar_wait(e.tfull0 + 8u * buf, (uint32_t)((e.j >> 1) & 1));
+        lk_wait(e.tfull0 + 8u * buf, (uint32_t)((e.j >> 1) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (e.pend_bar) {                                    // peers have finished reading the previous tile parked here
             mbar_wait_relaxed_cluster(e.pend_bar, e.pend_par);
@@ -321,10 +351,12 @@ __device__ __forceinline__ void epi_phase(const LayerPrm& prm, const int p, EpiC
         nmode++; e.j++;
     }
     if (p + 1 < prm.n_phases) {                              // publish this CTA's outputs, then arrive at the grid barrier
-        __threadfence();
-        asm volatile("fence.proxy.async;" ::: "memory");     // the next phase reads hn / hid through TMA (async proxy)
-        epi_bar();
-        if (threadIdx.x == 64) grid_arrive(prm.gbar, gridDim.x);
+        epi_bar();                                           // every epilogue thread's stores are ordered before thread 64 ...
+        if (threadIdx.x == 64) {                             // ... whose fence + release are cumulative (the grid.sync() pattern)
+            __threadfence();
+            asm volatile("fence.proxy.async;" ::: "memory"); // the next phase reads hn / hid through TMA (async proxy)
+            grid_arrive(prm.gbar, gridDim.x);
+        }
     }
 }
 
@@ -383,7 +415,7 @@ __global__ void __launch_bounds__(192, 1) gemm_layer_kernel(const __grid_constan
                 for (int i = 0; i < npre; i++) {             // immutable weights: requested before the dependency is met
                     const uint32_t g = it + (uint32_t)i;
                     const int slot = (int)(g % Cfg::STAGES);
-                    mbar_wait(empty_bar(slot), ((g / Cfg::STAGES) & 1) ^ 1);
+                    lk_wait(empty_bar(slot), ((g / Cfg::STAGES) & 1) ^ 1);
                     mbar_expect_tx(full_bar(slot), Cfg::STAGE_BYTES);
                     const int tile = (i / kbps) * geo.tpr + geo.off;
                     tma_load_2d(base + slot * Cfg::STAGE_BYTES, mp, full_bar(slot), (kb0 + i % kbps) * BK, tile * P_ROWS);
@@ -404,7 +436,7 @@ __global__ void __launch_bounds__(192, 1) gemm_layer_kernel(const __grid_constan
                 for (int i = npre; i < total; i++) {
                     const uint32_t g = it + (uint32_t)i;
                     const int slot = (int)(g % Cfg::STAGES);
-                    mbar_wait(empty_bar(slot), ((g / Cfg::STAGES) & 1) ^ 1);
+                    lk_wait(empty_bar(slot), ((g / Cfg::STAGES) & 1) ^ 1);
                     mbar_expect_tx(full_bar(slot), Cfg::STAGE_BYTES);
                     const int tile = (i / kbps) * geo.tpr + geo.off;
                     const uint32_t sp = base + slot * Cfg::STAGE_BYTES;
@@ -425,12 +457,12 @@ __global__ void __launch_bounds__(192, 1) gemm_layer_kernel(const __grid_constan
                 const int kbps = prm.kbps[p];
                 for (int a = 0; a < geo.n_act; a++, j++) {
                     const int buf = j & 1;
-                    mbar_wait(tempty0 + 8u * buf, (uint32_t)(((j >> 1) & 1) ^ 1));
+                    lk_wait(tempty0 + 8u * buf, (uint32_t)(((j >> 1) & 1) ^ 1));
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t acc = tmem_base + (uint32_t)(buf * QROWS);
                     for (int kb = 0; kb < kbps; kb++, it++) {
                         const int slot = (int)(it % Cfg::STAGES);
-                        mbar_wait(full_bar(slot), (it / Cfg::STAGES) & 1);
+                        lk_wait(full_bar(slot), (it / Cfg::STAGES) & 1);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         const uint32_t sp = base + slot * Cfg::STAGE_BYTES;
                         const uint64_t da = make_desc(sp), db = make_desc(sp + P_BYTES);
