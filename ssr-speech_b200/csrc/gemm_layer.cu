@@ -76,6 +76,12 @@ __device__ __forceinline__ void spin_guard(unsigned long long& t0) {
     if (t0 == 0) t0 = now;
     else if (now - t0 > LK_WATCHDOG_NS) __trap();
 }
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {       // non-blocking: has that phase completed?
+    uint32_t ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void lk_wait(uint32_t bar, uint32_t parity) {       // mbar_wait of tc_ptx.cuh with the watchdog
     uint32_t ok;
     unsigned long long t0 = 0;
@@ -404,6 +410,7 @@ __global__ void __launch_bounds__(192, 1) gemm_layer_kernel(const __grid_constan
             // ===== TMA producer: one ring across all phases; weights run ahead of the grid barrier, activations wait =====
             uint32_t it = 0;
             unsigned int gen0 = 0;
+            int carried = 0;                                 // weight stages of this phase already requested during the previous one
             for (int p = 0; p < prm.n_phases; p++) {
                 const PhaseGeo geo = phase_geo(prm, p, cluster, rank);
                 const int kbps = prm.kbps[p];
@@ -412,13 +419,31 @@ __global__ void __launch_bounds__(192, 1) gemm_layer_kernel(const __grid_constan
                 const CUtensorMap* mp = &maps.p[p];
                 const CUtensorMap* mq = &maps.q[p];
                 const int kb0 = geo.s * kbps;
-                for (int i = 0; i < npre; i++) {             // immutable weights: requested before the dependency is met
+                for (int i = carried; i < npre; i++) {       // immutable weights: requested before the dependency is met
                     const uint32_t g = it + (uint32_t)i;
                     const int slot = (int)(g % Cfg::STAGES);
                     lk_wait(empty_bar(slot), ((g / Cfg::STAGES) & 1) ^ 1);
                     mbar_expect_tx(full_bar(slot), Cfg::STAGE_BYTES);
                     const int tile = (i / kbps) * geo.tpr + geo.off;
                     tma_load_2d(base + slot * Cfg::STAGE_BYTES, mp, full_bar(slot), (kb0 + i % kbps) * BK, tile * P_ROWS);
+                }
+                carried = 0;
+                if (total < Cfg::STAGES && p + 1 < prm.n_phases) {
+                    // a phase shorter than the ring (out-proj: 4 k-blocks per CTA): the free stages take the NEXT phase's first
+                    // weight tiles before this phase's dependency is even met — at kernel entry that is HBM traffic issued
+                    // under the tail of the attention kernel.  Non-blocking: a stage that is still in use ends the run.
+                    const PhaseGeo gn = phase_geo(prm, p + 1, cluster, rank);
+                    const int kn = prm.kbps[p + 1];
+                    const int extra = min(gn.n_act * kn, Cfg::STAGES - total);
+                    for (int i = 0; i < extra; i++) {
+                        const uint32_t g = it + (uint32_t)(total + i);
+                        const int slot = (int)(g % Cfg::STAGES);
+                        if (!mbar_test(empty_bar(slot), ((g / Cfg::STAGES) & 1) ^ 1)) break;
+                        mbar_expect_tx(full_bar(slot), Cfg::STAGE_BYTES);
+                        const int tile = (i / kn) * gn.tpr + gn.off;
+                        tma_load_2d(base + slot * Cfg::STAGE_BYTES, &maps.p[p + 1], full_bar(slot), (gn.s * kn + i % kn) * BK, tile * P_ROWS);
+                        carried = i + 1;
+                    }
                 }
                 if (p == 0) {
                     pdl_wait();                              // attention output / residual stream of the preceding kernels

@@ -21,6 +21,15 @@ def test_protocol_terminates_and_reads_the_right_tiles():
     assert _sim().check(seeds=8, big=False) == 32
 
 
+def test_short_phase_prefetches_the_next_phase_weights():
+    m = _sim()
+    D, F = 512, 2048
+    sim = m.Sim(2, [D // 128, F // 128, D // 128, 3 * D // 128], [D // 64 // 8, D // 64 // 4, F // 64 // 8, D // 64 // 4], 2, 3, 4,
+                random.Random(0))
+    sim.run()
+    assert sim.n_carried == 16            # every CTA: out-proj fills 2 of 3 stages, the third takes FFN1's first weight tile
+
+
 def test_work_decomposition_covers_every_tile_slice_once():
     geo = _sim().geo
     for D, F, ncl in [(2048, 8192, 16), (512, 2048, 16), (1536, 6144, 11), (1024, 4096, 8)]:

@@ -71,6 +71,7 @@ class Sim:
         for c in self.ctas:
             self.threads += [self.producer(c), self.mma(c), self.umma_engine(c), self.epilogue(c)]
         self.launch_gen = 0
+        self.n_carried = 0                                # weight stages requested one phase ahead (short phases)
 
     def make_cta(self, i):
         c = type("CTA", (), {})()
@@ -94,7 +95,7 @@ class Sim:
 
     # ---- roles -------------------------------------------------------------------------------------------------------
     def producer(self, c):
-        it, gen0 = 0, None
+        it, gen0, carried = 0, None, 0
         for p in range(self.NP):
             S, gbase, s, n_act, tpr, off = geo(p, self.ncl, self.n_tiles[p], c.cluster, c.rank)
             kbps = self.kbps[p]
@@ -102,14 +103,28 @@ class Sim:
             npre = min(total, self.ST)
             kb0 = s * kbps
 
-            def tag(i):
+            def tag(i, p=p, kbps=kbps, tpr=tpr, off=off, kb0=kb0):
                 return (p, (i // kbps) * tpr + off, kb0 + i % kbps)
-            for i in range(npre):
+            for i in range(carried, npre):
                 g = it + i
                 slot = g % self.ST
                 yield lambda slot=slot, g=g: c.empty[slot].passed(((g // self.ST) & 1) ^ 1)
                 c.full[slot].expect_tx(2)
                 self.tma(c, slot, "P", tag(i))
+            carried = 0
+            if total < self.ST and p + 1 < self.NP:           # next phase's first weight tiles into the stages this phase leaves free
+                Sn, gbn, sn, n_actn, tprn, offn = geo(p + 1, self.ncl, self.n_tiles[p + 1], c.cluster, c.rank)
+                kn = self.kbps[p + 1]
+                for i in range(min(n_actn * kn, self.ST - total)):
+                    g = it + total + i
+                    slot = g % self.ST
+                    if not c.empty[slot].passed(((g // self.ST) & 1) ^ 1):
+                        break
+                    c.full[slot].expect_tx(2)
+                    self.tma(c, slot, "P", (p + 1, (i // kn) * tprn + offn, sn * kn + i % kn))
+                    carried = i + 1
+                    self.n_carried += 1
+                    yield lambda: True
             if p == 0:
                 gen0 = self.ggen                          # after griddepcontrol.wait
             else:
@@ -273,11 +288,14 @@ def check(seeds=60, verbose=False, big=True):
         n_tiles = [D // 128, F // 128, D // 128, 3 * D // 128][:nph]
         kbps = [D // 64 // 8, D // 64 // 4, F // 64 // 8, D // 64 // 4][:nph]
         n = seeds if ncl < 16 else max(2, seeds // 20)
+        carried = 0
         for seed in range(n):
-            steps = Sim(ncl, n_tiles, kbps, M, st, nph, random.Random(seed)).run()
+            sim = Sim(ncl, n_tiles, kbps, M, st, nph, random.Random(seed))
+            steps = sim.run()
+            carried += sim.n_carried
             total += 1
         if verbose:
-            print(f"n_clusters {ncl:>2}  D {D} F {F} M {M} stages {st} phases {nph}: {n} random schedules OK ({steps} events in the last)")
+            print(f"n_clusters {ncl:>2}  D {D} F {F} M {M} stages {st} phases {nph}: {n} random schedules OK ({steps} events in the last, {carried} stages requested a phase ahead)")
     return total
 
 
