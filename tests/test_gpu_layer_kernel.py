@@ -72,7 +72,7 @@ def _run_op(case, impl, out):
     return np.load(out)
 
 
-@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("case", CASES, ids=[f"M{m}-D{d}-F{f}-{'qkv' if q else 'last'}" for m, d, f, q in CASES])
 def test_layer_kernel_matches_per_gemm_chain(case, tmp_path):
     ref = _run_op(case, 0, str(tmp_path / "ref.npz"))
     got = _run_op(case, 1, str(tmp_path / "got.npz"))
