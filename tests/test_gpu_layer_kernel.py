@@ -10,7 +10,6 @@ residual stream x (adds only) must be BIT-identical; the LayerNorm-folded output
 of rstd*(acc - mean*colsum) + bias in two separately compiled bodies — tolerance 1e-5 x max|ref|, the same bar as
 test_gpu_gemm.py::test_dec_role_kernels_match_generic.
 """
-import json
 import os
 import subprocess
 import sys
