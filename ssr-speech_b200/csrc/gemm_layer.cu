@@ -163,7 +163,7 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-// one thread per CTA, after a CTA-level barrier behind the CTA's writers and a __threadfence() of its own
+// one thread per CTA, after a CTA-level barrier behind the CTA's writers (acq_rel: release of their stores, cumulative)
 __device__ __forceinline__ void grid_arrive(unsigned int* gbar, unsigned int n_cta) {
     unsigned int old;
     asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(gbar) : "memory");
@@ -358,10 +358,9 @@ __device__ __forceinline__ void epi_phase(const LayerPrm& prm, const int p, EpiC
     }
     if (p + 1 < prm.n_phases) {                              // publish this CTA's outputs, then arrive at the grid barrier
         epi_bar();                                           // every epilogue thread's stores are ordered before thread 64 ...
-        if (threadIdx.x == 64) {                             // ... whose fence + release are cumulative (the grid.sync() pattern)
-            __threadfence();
-            asm volatile("fence.proxy.async;" ::: "memory"); // the next phase reads hn / hid through TMA (async proxy)
-            grid_arrive(prm.gbar, gridDim.x);
+        if (threadIdx.x == 64) {                             // ... whose release is cumulative (the grid.sync() pattern; the
+            asm volatile("fence.proxy.async;" ::: "memory"); // acq_rel atomic of grid_arrive carries the GPU-scope fence).  The
+            grid_arrive(prm.gbar, gridDim.x);                // next phase reads hn / hid through TMA: async-proxy fence first
         }
     }
 }
