@@ -381,6 +381,8 @@ __global__ void __launch_bounds__(192, 1) gemm_layer_kernel(const __grid_constan
 
     pdl_launch_dependents();
     __shared__ float s_mu[P_ROWS], s_rs[P_ROWS];
+    __shared__ volatile unsigned int s_gen0[2];              // {generation of the grid barrier at kernel entry, valid}
+    if (threadIdx.x == 0) s_gen0[1] = 0u;                    // (ordered before every reader by the __syncthreads below)
     const int ts = ts_begin(TSK_GEMM);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rank = (int)cluster_ctarank();
@@ -447,8 +449,15 @@ __global__ void __launch_bounds__(192, 1) gemm_layer_kernel(const __grid_constan
                 if (p == 0) {
                     pdl_wait();                              // attention output / residual stream of the preceding kernels
                     ts_dep(ts);
-                    gen0 = ld_acquire_gpu(prm.gbar + 32);
                 } else {
+                    if (p == 1) {
+                        // the base generation is read ONCE per CTA, by the thread that later arrives for this CTA (thread 64):
+                        // a second read here could come after barrier 0 has already completed (a CTA without work in phase 0
+                        // arrives immediately) and would then wait for a generation that needs this very thread to progress
+                        unsigned long long t0 = 0;
+                        while (s_gen0[1] == 0u) spin_guard(t0);
+                        gen0 = s_gen0[0];
+                    }
                     grid_wait(prm.gbar, gen0 + (unsigned int)p);
                     ts_aux(ts, p - 1);
                 }
@@ -506,7 +515,13 @@ __global__ void __launch_bounds__(192, 1) gemm_layer_kernel(const __grid_constan
         e.parked8 = parked8; e.parked4 = parked4; e.cons8 = cons8; e.cons4 = cons4;
         e.pend_bar = 0; e.pend_par = 0; e.j = 0; e.n8 = 0; e.n4 = 0;
         e.cluster = cluster; e.rank = rank; e.warp = warp; e.lane = lane;
-        e.gen0 = threadIdx.x == 64 ? ld_acquire_gpu(prm.gbar + 32) : 0u;
+        e.gen0 = 0u;
+        if (threadIdx.x == 64) {                             // after griddepcontrol.wait: every earlier launch has completed
+            e.gen0 = ld_acquire_gpu(prm.gbar + 32);
+            s_gen0[0] = e.gen0;
+            __threadfence_block();
+            s_gen0[1] = 1u;
+        }
         for (int p = 0; p < prm.n_phases; p++) {
             switch (p) {
                 case 1: epi_phase<QROWS, LK_FFN1>(prm, p, e, s_mu, s_rs); break;

@@ -88,6 +88,7 @@ class Sim:
         c.park = None
         c.umma_q = []                                     # in-order queue of issued MMAs / commits
         c.done = False
+        c.gen0 = None
         return c
 
     def peer(self, c, rank):
@@ -125,9 +126,10 @@ class Sim:
                     carried = i + 1
                     self.n_carried += 1
                     yield lambda: True
-            if p == 0:
-                gen0 = self.ggen                          # after griddepcontrol.wait
-            else:
+            if p > 0:
+                if p == 1:                                # base generation: read once per CTA, by the arriving (epilogue) thread
+                    yield lambda: c.gen0 is not None
+                    gen0 = c.gen0
                 yield lambda p=p: self.ggen - (gen0 + p) >= 0
             for i in range(npre):
                 slot = (it + i) % self.ST
@@ -194,7 +196,7 @@ class Sim:
         consumed-arrivals are issued as 4 separate arrivals"""
         j, n = 0, {8: 0, 4: 0}
         pend = None
-        gen0 = self.ggen
+        gen0 = c.gen0 = self.ggen
         for p in range(self.NP):
             S, gbase, s, n_act, tpr, off = geo(p, self.ncl, self.n_tiles[p], c.cluster, c.rank)
             kbps = self.kbps[p]
