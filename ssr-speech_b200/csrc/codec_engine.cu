@@ -70,6 +70,7 @@ int ssrb_codec_create(const ssrb_codec_config* c, int device, ssrb_codec** out) 
     SSRB_CHECK(c->n_q <= 16 && c->dimension <= 128 && c->dimension % 16 == 0, "codec: unsupported RVQ geometry");
     SSRB_CUDA(cudaSetDevice(device));
     ssrb_codec* cd = new ssrb_codec();
+    struct Guard { ssrb_codec* p; ~Guard() { if (p) ssrb_codec_destroy(p); } } guard{cd};   // an allocation failure below frees what exists
     cd->cfg = *c; cd->device = device;
     cd->use_tc = c->tensor_cores != 0;
     if (cd->cfg.max_batch_chunk <= 0 || cd->cfg.max_batch_chunk > 32) cd->cfg.max_batch_chunk = 8;
@@ -79,6 +80,7 @@ int ssrb_codec_create(const ssrb_codec_config* c, int device, ssrb_codec** out) 
     SSRB_TRY(dalloc((void**)&cd->cb_sq, (size_t)c->n_q * c->bins * 4));
     SSRB_TRY(dalloc((void**)&cd->wm_embed, 2 * (c->dimension / 16) * 4));
     SSRB_TRY(dalloc((void**)&cd->bar, 4));
+    guard.p = nullptr;
     *out = cd;
     return 0;
 }

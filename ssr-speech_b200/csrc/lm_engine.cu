@@ -132,6 +132,7 @@ int ssrb_lm_create(const ssrb_lm_config* c, int device, ssrb_lm** out) {
     SSRB_CHECK(c->max_rows > 0 && c->max_seq > 0 && c->max_prefill_tokens > 0 && c->max_steps > 0, "bad capacity");
     SSRB_CUDA(cudaSetDevice(device));
     ssrb_lm* lm = new ssrb_lm();
+    struct Guard { ssrb_lm* p; ~Guard() { if (p) ssrb_lm_destroy(p); } } guard{lm};    // an allocation failure below frees what exists
     lm->cfg = *c; lm->device = device;
     lm->D = c->d_model; lm->H = c->n_head; lm->L = c->n_layer; lm->F = c->ffn_dim; lm->K = c->n_codebooks;
     lm->V = c->n_audio_tokens; lm->Vt = c->n_text_tokens; lm->Hh = c->head_hidden;
@@ -196,6 +197,7 @@ int ssrb_lm_create(const ssrb_lm_config* c, int device, ssrb_lm** out) {
     SSRB_TRY(dev_alloc((void**)&lm->d_iter, 4));
     SSRB_TRY(dev_alloc((void**)&lm->gbar, 64 * 4));
     SSRB_CUDA(cudaMemset(lm->gbar, 0, 64 * 4));
+    guard.p = nullptr;
     *out = lm;
     return 0;
 }
