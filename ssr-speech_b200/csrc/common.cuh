@@ -86,7 +86,7 @@ struct TsBuf { unsigned long long* buf; unsigned int* idx; unsigned int cap; };
 static __device__ TsBuf g_ts = {nullptr, nullptr, 0};      // one copy per translation unit (no -rdc); armed by ts_arm_tu()
 static inline int ts_arm_tu(const TsBuf& t) { return cudaMemcpyToSymbol(g_ts, &t, sizeof(t)) == cudaSuccess ? 0 : 1; }
 int ts_arm_gemm_tc(const TsBuf& t); int ts_arm_attn_tma(const TsBuf& t); int ts_arm_lm_kernels(const TsBuf& t);
-int ts_arm_gemm_layer(const TsBuf& t);
+int ts_arm_gemm_layer(const TsBuf& t); int ts_arm_gemm_flat2(const TsBuf& t);
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -205,6 +205,11 @@ int gemm_simt(const GemmArgs& g, cudaStream_t stream);
 int gemm_tc(const GemmArgs& g, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 size_t gemm_tc_workspace_bytes(int max_rows_decode, int max_n);
 bool gemm_tc_supported(const GemmArgs& g);
+
+// ---- prefill GEMM on CTA pairs (gemm_flat2.cu; experimental, SSRB_FLAT_2CTA=1): tcgen05.mma.cta_group::2, 256 x 256 tiles --------
+bool gemm_flat2_enabled();
+bool gemm_flat2_supported(const GemmArgs& g);
+int gemm_flat2(const GemmArgs& g, cudaStream_t stream);
 
 // ---- persistent per-layer decode GEMM chain (gemm_layer.cu; experimental, SSRB_LAYER_KERNEL=1) ---------------------------
 // One launch runs the GEMMs between two attention kernels of a decode iteration with the LayerNorms folded exactly as the

@@ -828,7 +828,7 @@ int ssrb_lm_profile_steps(ssrb_lm* lm, int n_steps, void* stream, double* ms_by_
 
 int ssrb_debug_timeline(unsigned long long* dev_buf, unsigned int* dev_idx, unsigned int cap) {
     TsBuf t{dev_buf, dev_idx, cap};
-    SSRB_CHECK(!ts_arm_gemm_tc(t) && !ts_arm_attn_tma(t) && !ts_arm_lm_kernels(t) && !ts_arm_gemm_layer(t), "cudaMemcpyToSymbol failed");
+    SSRB_CHECK(!ts_arm_gemm_tc(t) && !ts_arm_attn_tma(t) && !ts_arm_lm_kernels(t) && !ts_arm_gemm_layer(t) && !ts_arm_gemm_flat2(t), "cudaMemcpyToSymbol failed");
     return 0;
 }
 

@@ -1,12 +1,24 @@
 #!/bin/bash
-# Round-2 bring-up of the experimental persistent per-layer GEMM kernel (csrc/gemm_layer.cu) on one B200:
-#   1. the gated parity tests (every case in a child process under a timeout: a broken grid barrier hangs, it does not crash);
-#   2. if green, a bench A/B of the default chain against SSRB_LAYER_KERNEL=1 with the in-kernel timeline of both.
-# Usage:  gpurun --timeout 1500 -- 'bash tools/gpu_layer_ab.sh'
+# Round-2 bring-up of the two experimental kernels on one B200 (both off by default, neither has run on hardware yet):
+#   A. persistent per-layer decode GEMM kernel (csrc/gemm_layer.cu, SSRB_LAYER_KERNEL=1)
+#   B. CTA-pair prefill GEMM (csrc/gemm_flat2.cu, SSRB_FLAT_2CTA=1)
+# For each: the gated parity tests first (every case in a child process under a timeout; the kernels' spins trap after 2 s, so a
+# protocol bug fails a launch instead of hanging the box), and only if they are green a same-box bench A/B with in-kernel timelines.
+# Usage:  gpurun --timeout 2400 -- 'bash tools/gpu_layer_ab.sh'        (SECTIONS="A" or "B" to run one)
 set -u
 mkdir -p gpurun_out
-SSRB_EXPERIMENTAL=1 timeout 1200 python -m pytest tests/test_gpu_layer_kernel.py -m gpu -x -q > gpurun_out/pytest_layer.log 2>&1
-rc=$?; echo "pytest rc=$rc" >> gpurun_out/pytest_layer.log
-tail -15 gpurun_out/pytest_layer.log
-if [ $rc -ne 0 ]; then echo "layer kernel parity failed: no A/B"; exit $rc; fi
-bash tools/gpu_ab.sh base:SSRB_LAYER_KERNEL=0,TL=1 layer:SSRB_LAYER_KERNEL=1,TL=1
+SECTIONS=${SECTIONS:-"A B"}
+if [[ " $SECTIONS " == *" A "* ]]; then
+  SSRB_EXPERIMENTAL=1 timeout 1200 python -m pytest tests/test_gpu_layer_kernel.py -m gpu -x -q > gpurun_out/pytest_layer.log 2>&1
+  rc=$?; echo "pytest rc=$rc" >> gpurun_out/pytest_layer.log
+  tail -15 gpurun_out/pytest_layer.log
+  if [ $rc -eq 0 ]; then bash tools/gpu_ab.sh base:SSRB_LAYER_KERNEL=0,TL=1 layer:SSRB_LAYER_KERNEL=1,TL=1
+  else echo "layer kernel parity failed: no A/B"; fi
+fi
+if [[ " $SECTIONS " == *" B "* ]]; then
+  SSRB_EXPERIMENTAL=1 timeout 1200 python -m pytest tests/test_gpu_flat2.py -m gpu -x -q > gpurun_out/pytest_flat2.log 2>&1
+  rc=$?; echo "pytest rc=$rc" >> gpurun_out/pytest_flat2.log
+  tail -8 gpurun_out/pytest_flat2.log
+  if [ $rc -eq 0 ]; then bash tools/gpu_ab.sh base2:SSRB_FLAT_2CTA=0 pair:SSRB_FLAT_2CTA=1      # compare "lm_prefill_ms" of the two lines
+  else echo "CTA-pair GEMM parity failed: no A/B"; fi
+fi
