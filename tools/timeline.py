@@ -39,7 +39,13 @@ def main():
         dep = np.where(r[:, 3] > 0, r[:, 3], r[:, 2])
         line = (f"{i:3d} {timeline.KERNELS[kid]:9s} ctas={len(r):5d} first_start={(r[:, 2].min() - t0) / 1e3:9.2f} "
                 f"dep={(dep.min() - t0) / 1e3:9.2f} last_exit={(r[:, 4].max() - t0) / 1e3:9.2f} dep->exit={(r[:, 4].max() - dep.min()) / 1e3:7.2f}")
-        if kid == 3:
+        if kid == 3 and not r[:, 8].any() and not r[:, 9].any() and r[:, 5].any() and len(r) >= 64:
+            # persistent per-layer kernel (gemm_layer.cu, SSRB_LAYER_KERNEL=1): aux0..2 = producer thread past grid barrier 1..3
+            d = dep.astype(np.float64)
+            med = lambda a: float(np.median(a[a > 0])) / 1e3 if (a > 0).any() else float("nan")
+            line += (f" | LAYER kernel, medians after dep: past_barrier1={med(r[:, 5] - d):6.2f} past_barrier2={med(r[:, 6] - d):6.2f} "
+                     f"past_barrier3={med(r[:, 7] - d):6.2f} exit={med(r[:, 4] - d):6.2f} start={float(np.median(r[:, 2] - d)) / 1e3:6.2f}")
+        elif kid == 3:
             d = dep.astype(np.float64)
             med = lambda a: float(np.median(a)) / 1e3
             line += (f" | medians after dep: loads_issued={med(r[:, 5] - d):5.2f} accum={med(r[:, 6] - d):5.2f} parked={med(r[:, 7] - d):5.2f} "
