@@ -280,7 +280,9 @@ def run_reference_arm(args):
 
 def workload_config(args):
     T = int(round(args.prompt_sec * 50))
-    return {"workload": f"BASELINE configs[2]: English TTS 830M random-init, cfg_coef=1.5 cfg_stride=5 aug_text, top_p=0.8, "
+    exp = {k: os.environ[k] for k in ("SSRB_LAYER_KERNEL", "SSRB_FLAT_2CTA") if os.environ.get(k, "0") not in ("", "0")}
+    return {**({"experimental_switches": exp} if exp else {}),      # A/B lines of kernels that are off by default name themselves
+            "workload": f"BASELINE configs[2]: English TTS 830M random-init, cfg_coef=1.5 cfg_stride=5 aug_text, top_p=0.8, "
                         f"{args.prompt_sec:g} s prompt -> {(10 * args.lx - T - 9) / 50:g} s generation, batch {args.batch}/GPU",
             "batch_per_gpu": args.batch, "prompt_frames": T, "text_len": args.lx, "rows_per_gpu": 2 * args.batch,
             "precision": args.precision, "codec_decoder_precision": args.codec_precision, "watermark_decode": not args.no_watermark,
