@@ -61,5 +61,31 @@ def build(force: bool = False, verbose: bool = False, extra_flags=()) -> str:
     return LIB
 
 
+def build_variant(out: str, defines) -> str:
+    """A second library with extra -D macros (e.g. LK_STRONG_SYNC=1, DEC_STAGES=3) for same-box A/B runs: select it with
+    SSRB_LIB=<out> (tools/gpu_ab.sh).  Objects go to a scratch directory; the in-tree library is untouched."""
+    import tempfile
+    tmp = tempfile.mkdtemp(prefix="ssrb_variant_")
+    objs, procs = [], []
+    for src in SOURCES:
+        obj = os.path.join(tmp, src.replace(".cu", ".o"))
+        objs.append(obj)
+        cmd = [_nvcc(), *[f for f in NVCC_FLAGS if f != "--use_fast_math=false"], *[f"-D{d}" for d in defines], "-c",
+               os.path.join(CSRC, src), "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for src, p in procs:
+        o, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src}:\n{o}")
+    r = subprocess.run([_nvcc(), "-shared", "-o", out, *objs, "-lcudart"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}")
+    return out
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True, extra_flags=["-Xptxas", "-v"] if "--ptxas" in sys.argv else []))
+    if "--variant" in sys.argv:          # python build.py --variant out.so LK_STRONG_SYNC=1 [MORE=...]
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+    else:
+        print(build(force="--force" in sys.argv, verbose=True, extra_flags=["-Xptxas", "-v"] if "--ptxas" in sys.argv else []))
