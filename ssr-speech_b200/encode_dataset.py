@@ -35,11 +35,12 @@ def parse_args(argv=None):
     return p.parse_args(argv)
 
 
-def write_array_to_txt_file(array, filename):
-    with open(filename, "w") as f:
-        for a in array[:-1]:
-            f.write(" ".join(map(str, a)) + "\n")
-        f.write(" ".join(map(str, array[-1])))
+def write_code_rows(codes, path: str) -> None:
+    """The on-disk format of data/encode.py:53-57: one line per codebook, codes separated by single spaces, no newline after the
+    last line."""
+    text = "\n".join(" ".join(str(int(c)) for c in row) for row in codes)
+    with open(path, "w") as f:
+        f.write(text)
 
 
 def encode_items(tokenizer: AudioTokenizer, items, save_root: str, batch_size: int, model_sr: int, code_sr: int):
@@ -64,7 +65,7 @@ def encode_items(tokenizer: AudioTokenizer, items, save_root: str, batch_size: i
         for i, d in enumerate(durs):
             fn = os.path.join(save_root, ids[i] + ".txt")
             if not os.path.exists(fn):
-                write_array_to_txt_file(codes[i, :, :round(d * code_sr)].tolist(), fn)
+                write_code_rows(codes[i, :, :round(d * code_sr)].tolist(), fn)
                 n_done += 1
     return n_done
 

@@ -98,3 +98,13 @@ def test_conv_and_convtr_length_rules(k, s, T):
     if k == 2 * s:
         z = o.convtr(x, "t.", s)
         assert z.shape[-1] == T * s
+
+
+def test_code_file_format(tmp_path):
+    """data/encode.py:53-57: K lines of space-separated integers, no trailing newline."""
+    from ssr_speech_b200.encode_dataset import write_code_rows
+    fn = tmp_path / "seg.txt"
+    write_code_rows([[1, 22, 333], [4, 5, 6]], str(fn))
+    assert fn.read_text() == "1 22 333\n4 5 6"
+    write_code_rows(np.asarray([[7, 8]]).tolist(), str(fn))
+    assert fn.read_text() == "7 8"
