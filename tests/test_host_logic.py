@@ -108,3 +108,28 @@ def test_code_file_format(tmp_path):
     assert fn.read_text() == "1 22 333\n4 5 6"
     write_code_rows(np.asarray([[7, 8]]).tolist(), str(fn))
     assert fn.read_text() == "7 8"
+
+
+def test_audio_plumbing_matches_reference_rules(tmp_path):
+    """data/tokenizer.py:87-97,141-159: zero-pad to a multiple of 320, stereo -> mono by averaging, mono stays, 16 kHz is not resampled;
+    the wav reader returns float32 [C, T] in [-1, 1) like torchaudio.load."""
+    from scipy.io import wavfile
+    from ssr_speech_b200.codec import convert_audio, load_wav, pad_to_multiple
+    rng = np.random.default_rng(0)
+    pcm = (rng.standard_normal((1000, 2)) * 8000).astype(np.int16)
+    fn = str(tmp_path / "a.wav")
+    wavfile.write(fn, 16000, pcm)
+    wav, sr = load_wav(fn)
+    assert sr == 16000 and wav.dtype == torch.float32 and tuple(wav.shape) == (2, 1000)
+    assert torch.allclose(wav, torch.from_numpy(pcm.T.astype(np.float32) / 32768.0))
+    part, _ = load_wav(fn, offset=100, num_frames=300)
+    assert torch.equal(part, wav[:, 100:400])
+    padded = pad_to_multiple(wav, 320)
+    assert padded.shape[-1] == 1280 and torch.equal(padded[:, :1000], wav) and not padded[:, 1000:].any()
+    assert pad_to_multiple(padded, 320) is padded                       # already a multiple: untouched
+    mono = convert_audio(padded, 16000, 16000, 1)
+    assert tuple(mono.shape) == (1, 1280) and torch.allclose(mono[0], padded.mean(0))
+    assert torch.equal(convert_audio(mono, 16000, 16000, 1), mono)
+    assert tuple(convert_audio(mono, 16000, 16000, 2).shape) == (2, 1280)
+    with pytest.raises(AssertionError):
+        convert_audio(torch.zeros(3, 640), 16000, 16000, 1)
