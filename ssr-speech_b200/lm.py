@@ -295,7 +295,11 @@ class SSR_Speech:
             _lib.check(lib.ssrb_lm_begin(self._h, C.byref(batch), C.byref(sp),
                                          C.c_void_p(noise_dev.data_ptr()) if noise_dev is not None else None, st), "ssrb_lm_begin")
             ev1.record()
-        return {"U": U, "preps": preps, "dev": dev, "ev0": ev0, "ev1": ev1}
+        # Exact upper bound on the loop iterations of this batch (the prefill's sample counts as iteration 1): the reference's
+        # length guard (ssr.py:739) forces EOG at the latest after seq.expected_steps() iterations of a span, and a later span
+        # starts from a longer sequence, so it can only be shorter.
+        bound = max(preps[i].num_spans * seq.expected_steps(cfg, x_lens[i], preps[i].prompt_tokens.shape[1]) for i in range(U))
+        return {"U": U, "preps": preps, "dev": dev, "ev0": ev0, "ev1": ev1, "bound": bound}
 
     @torch.no_grad()
     def inference_batch(self, xs, ys, mask_intervals, poll_every: Optional[int] = None, **kw):
@@ -315,7 +319,10 @@ class SSR_Speech:
                 _lib.check(lib.ssrb_lm_poll(self._h, st, C.byref(nd), C.byref(it)), "ssrb_lm_poll")
                 if nd.value >= U or it.value >= self._cap[3] + 1:
                     break
-                _lib.check(lib.ssrb_lm_decode(self._h, int(poll_every), st), "ssrb_lm_decode")
+                # never enqueue past the last iteration the batch can need: an iteration after the last EOG still streams
+                # every weight (8 of 513 iterations of the bench batch were such overshoot with a fixed chunk of 16)
+                n = min(poll_every, max(1, ob["bound"] - it.value))
+                _lib.check(lib.ssrb_lm_decode(self._h, int(n), st), "ssrb_lm_decode")
             ev2.record()
             torch.cuda.synchronize()
             self.last_stats = {"prefill_ms": ob["ev0"].elapsed_time(ob["ev1"]), "decode_ms": ob["ev1"].elapsed_time(ev2),

@@ -113,3 +113,22 @@ def test_repetition_fixtures_exercise_the_penalty_branch(gold_dir, name):
     assert penalty_steps(g, cfg_tiny().eog) >= 1
     for other in ("tts_greedy", "edit_cfg_sampled", "tts_cfg_temp_topk"):
         assert penalty_steps(np.load(os.path.join(gold_dir, f"lm_{other}.npz")), cfg_tiny().eog) == 0
+
+
+@pytest.mark.parametrize("name", LM_CASES)
+def test_iteration_bound_covers_the_reference_rollouts(gold_dir, name):
+    """lm.SSR_Speech caps its last chunk of decode iterations at n_spans * seq.expected_steps(...) (the reference's length guard,
+    ssr.py:739, bounds every span): the bound must cover every roll-out the reference produced, and be exact when the guard
+    ends a single span."""
+    cfg = cfg_tiny()
+    g = np.load(os.path.join(gold_dir, f"lm_{name}.npz"))
+    kw = json.loads(str(g["kw"]))
+    x, y, out_len = g["x"], g["y"].T.copy(), 0
+    if kw.get("aug_context") and sum(b - a for a, b in g["mask_interval"].tolist()) < 2 * 50:
+        x, y, out_len = np.concatenate([g["prompt_x"], x]), np.concatenate([g["prompt"].T, y], 1), g["prompt"].shape[0]
+    prep = seq.prepare(cfg, y, g["mask_interval"].tolist(), out_len=out_len)
+    bound = prep.num_spans * seq.expected_steps(cfg, len(x), prep.prompt_tokens.shape[1])
+    total = int(g["ref_span_lens"].sum())
+    assert total <= bound, (total, bound)
+    if prep.num_spans == 1 and g["ref_span_tokens"][-cfg.n_codebooks, 0] == cfg.eog and total == bound:
+        assert g["ref_span_lens"][0] == seq.expected_steps(cfg, len(x), prep.prompt_tokens.shape[1])

@@ -73,6 +73,8 @@ def run_case(pair, seed, T, Lx, spans, kw, ctx=None):
     torch.manual_seed(seed)
     got = oracle.inference(xo, torch.from_numpy(prep.prompt_tokens), prep.num_spans, silence_tokens=SILENCE,
                            incremental=bool(kw["kvcache"]), **okw)
+    # the iteration bound lm.SSR_Speech uses to size its last chunk of decode iterations covers the reference's roll-out
+    assert sum(len(sp) for sp in got) <= prep.num_spans * seq.expected_steps(cfg, xo.shape[0], prep.prompt_tokens.shape[1])
     ores, omarks, omasks, onmi = seq.finalize(cfg, prep, got)
     tag = (seed, T, Lx, spans, kw, ctx)
     assert ores.shape == tuple(res[0].shape), tag
