@@ -321,8 +321,7 @@ class SSR_Speech:
                     break
                 # never enqueue past the last iteration the batch can need: an iteration after the last EOG still streams
                 # every weight (8 of 513 iterations of the bench batch were such overshoot with a fixed chunk of 16)
-                n = min(poll_every, max(1, ob["bound"] - it.value))
-                _lib.check(lib.ssrb_lm_decode(self._h, int(n), st), "ssrb_lm_decode")
+                _lib.check(lib.ssrb_lm_decode(self._h, self._next_chunk(poll_every, ob["bound"], it.value), st), "ssrb_lm_decode")
             ev2.record()
             torch.cuda.synchronize()
             self.last_stats = {"prefill_ms": ob["ev0"].elapsed_time(ob["ev1"]), "decode_ms": ob["ev1"].elapsed_time(ev2),
@@ -332,6 +331,12 @@ class SSR_Speech:
                 res, marks, masks, nmi = self._collect(i, preps[i])
                 results.append((res.to(dev) if dev is not None else res, marks, masks, nmi))
         return results
+
+    @staticmethod
+    def _next_chunk(poll_every: int, bound: int, done_iterations: int) -> int:
+        """Iterations to enqueue before the next poll: `poll_every`, but never past `bound` (the last iteration the batch can
+        need); at least 1, so a bound that was too small could only slow the loop down, never end it early."""
+        return int(min(poll_every, max(1, bound - done_iterations)))
 
     def _collect(self, slot: int, prep):
         """Reads the sampled tokens of one finished slot and runs the epilogue (ssr.py:774-812)."""

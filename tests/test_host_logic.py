@@ -133,3 +133,17 @@ def test_audio_plumbing_matches_reference_rules(tmp_path):
     assert tuple(convert_audio(mono, 16000, 16000, 2).shape) == (2, 1280)
     with pytest.raises(AssertionError):
         convert_audio(torch.zeros(3, 640), 16000, 16000, 1)
+
+
+def test_decode_chunk_schedule_stops_at_the_iteration_bound():
+    """lm.SSR_Speech.inference_batch polls `done` every poll_every iterations; the last chunk is cut at the batch's iteration bound
+    (bench batch: 505 iterations, the prefill's sample being the first) instead of overshooting to 513."""
+    from ssr_speech_b200.lm import SSR_Speech
+    it, chunks = 1, []
+    while it < 505:
+        n = SSR_Speech._next_chunk(16, 505, it)
+        chunks.append(n)
+        it += n
+    assert it == 505 and chunks[:-1] == [16] * 31 and chunks[-1] == 8
+    assert SSR_Speech._next_chunk(16, 505, 505) == 1 and SSR_Speech._next_chunk(16, 10, 400) == 1     # past the bound: keep stepping
+    assert SSR_Speech._next_chunk(1, 505, 3) == 1
