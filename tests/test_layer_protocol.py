@@ -10,8 +10,12 @@ import pytest
 from conftest import ROOT
 
 
-def _sim():
-    spec = importlib.util.spec_from_file_location("layer_protocol_sim", os.path.join(ROOT, "tools", "layer_protocol_sim.py"))
+def _sim(name="layer_protocol_sim"):
+    import sys
+    tools = os.path.join(ROOT, "tools")
+    if tools not in sys.path:
+        sys.path.insert(0, tools)                          # flat2_protocol_sim imports the barrier model of layer_protocol_sim
+    spec = importlib.util.spec_from_file_location(name, os.path.join(tools, name + ".py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod
@@ -56,3 +60,20 @@ def test_model_detects_a_missing_wait():
     exec(compile(broken, "broken_sim", "exec"), ns)
     with pytest.raises(AssertionError):
         ns["check"](seeds=6, big=False)
+
+
+def test_cta_pair_gemm_protocol():
+    """csrc/gemm_flat2.cu: both CTAs' TMA loads complete on the leader's barrier (possibly before the leader armed it), multicast
+    commits, both epilogues release the leader's accumulator barrier."""
+    assert _sim("flat2_protocol_sim").check(seeds=15) == 75
+
+
+def test_cta_pair_model_detects_a_wrong_arrival_count():
+    src = open(os.path.join(ROOT, "tools", "flat2_protocol_sim.py")).read()
+    broken = src.replace("c.tempty = [MBar(8), MBar(8)]", "c.tempty = [MBar(4), MBar(4)]")      # forgets the peer's epilogue warps
+    assert broken != src
+    _sim()                                                   # puts tools/ on sys.path for the import inside the model
+    ns = {"__name__": "broken_flat2"}
+    exec(compile(broken, "broken_flat2", "exec"), ns)
+    with pytest.raises(AssertionError):
+        ns["check"](seeds=10)

@@ -41,9 +41,8 @@ class MBar:
         self.arrive()
 
     def complete_tx(self, nbytes):
-        self.tx -= nbytes
-        assert self.tx >= 0
-        self._maybe_flip()
+        self.tx -= nbytes                 # may go negative: bytes can land before the matching expect_tx (PTX: tx-count is signed);
+        self._maybe_flip()                # the phase still needs the pending arrival that comes with the expect_tx
 
     def passed(self, parity):             # try_wait.parity: the phase with this parity has completed
         return self.phase != parity
