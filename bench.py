@@ -340,10 +340,12 @@ def main():
     tokens_per_step = args.batch * K_CODEBOOKS * gen_frames            # per rank
 
     def step_host(timings):
+        # N > 1: the finished waveforms stay in HBM, ONE NCCL all_gather over NVLink, then ONE device-to-host copy
         out, results = pipeline.inference_batch(model, tok, wavs, texts, spans, dc, cfg_coef=1.5, cfg_stride=5, aug_text=True,
-                                                use_watermark=not args.no_watermark, tts=True, seed=1000, timings=timings)
+                                                use_watermark=not args.no_watermark, tts=True, seed=1000, timings=timings,
+                                                to_host=(world == 1))
         if world > 1:
-            out = gather_waveforms([o.to(dev) for o in out], device=dev)
+            out = gather_waveforms(out, device=dev, to_host=True)
         return out, results
 
     def barrier():
@@ -377,7 +379,8 @@ def main():
     launches = lib.ssrb_launch_count() - launches0
     h2d = sum(w.numel() * 4 for w in wavs) + sum(t.numel() * 4 for t in texts) * 2 \
         + args.batch * (T // 320 + gen_frames) * 320 * 4 * (0 if args.no_watermark else 1)
-    d2h = sum(o.numel() * 4 for o in out[:args.batch]) + args.batch * K_CODEBOOKS * (gen_frames + 4) * 4
+    # per rank: its own waveforms at N = 1; at N > 1 every rank reads the whole gathered job back in one copy
+    d2h = sum(o.numel() * 4 for o in out) + args.batch * K_CODEBOOKS * (gen_frames + 4) * 4
 
     # ---- timed region B: inputs resident in HBM (value) ----------------------------------------------------------------------
     wav_dev = torch.stack(wavs, 0).to(dev)

@@ -228,6 +228,20 @@ int ssrb_op_layer_chain(const void* ao_dev, float* x_inout_dev, const void* wo_d
                         const float* beta1n_dev, void* hid_out_dev, float* qkv_out_dev, int M, int D, int F, int impl,
                         void* stream);
 
+/* Single-query attention against the in-place bf16 cache exactly as the decode chain runs it (replaces
+ * F.scaled_dot_product_attention at models/modules/activation.py:634 for tgt_len == 1 plus the cache re-materialisation of
+ * activation.py:626-631): qkv_dev fp32 [R, 3D] (q | k | v of this step), caches bf16 [R][H][Smax][128] holding seq_len[r]
+ * keys per row; the kernel appends this step's K/V row at slot seq_len[r] and writes out_dev bf16 [R, D].  seq_len_host /
+ * done_host (may be NULL) are HOST arrays [R]; rows with done != 0 are skipped.  Synchronises. */
+int ssrb_op_attn_decode(const float* qkv_dev, void* kcache_dev, void* vcache_dev, const int32_t* seq_len_host,
+                        const int32_t* done_host, void* out_dev, int R, int D, int H, int Smax, void* stream);
+
+/* Causal prefill attention over packed rows exactly as the bf16 prefill runs it (activation.py:634 for the first
+ * dec_forward, models/ssr.py:673-684): qkv_dev fp32 [sum(row_len), 3D]; K/V are first scattered into the caches
+ * (row i -> cache row i, slot = position), then every position attends to positions <= its own.  out_dev bf16 [sum, D]. */
+int ssrb_op_attn_prefill(const float* qkv_dev, void* kcache_dev, void* vcache_dev, const int32_t* row_len_host, int n_rows,
+                         void* out_dev, int D, int H, int Smax, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -200,7 +200,7 @@ def run_codec_cases():
     np.savez_compressed(os.path.join(GOLD, "codec_small.npz"), wav=wav.numpy(), weights_seed=3,
                         codebook_mu=mu.numpy(), codebook_sigma=sigma.numpy(), ref_emb=emb.numpy(), ref_codes=codes.numpy(),
                         ref_dec=dec.numpy(), marks=marks.numpy(), ref_wm=wm.numpy(), ref_mark_logits=mlog.numpy())
-    # config 1 of BASELINE.json: demo wav round trip (first 2 s stored; full-length checked here only)
+    # config 1 of BASELINE.json: demo wav round trip, full length (126 880 samples -> 127 040 -> 397 frames)
     try:
         from scipy.io import wavfile
         sr, data = wavfile.read(os.path.join(ref_loader.REF_ROOT, "demo", "84_121550_000074_000000.wav"))
@@ -215,14 +215,18 @@ def run_codec_cases():
         print(f"[codec] demo wav sr={sr} len={data.shape[-1]} frames={c_full.shape[-1]} "
               f"codes_equal={bool(torch.equal(oc, c_full))} emb_err={(oe - e_full).abs().max().item():.3e} "
               f"dec_err={(od - d_full).abs().max().item():.3e}")
-        n = 32000
-        seg = data[..., :n]
+        # BASELINE configs[0]: the WHOLE demo utterance (397 frames), decode and wmdecode with marks[100:200] = 1
+        marks_full = torch.zeros(1, c_full.shape[-1], dtype=torch.long)
+        marks_full[0, 100:200] = 1
         with torch.no_grad():
-            c_seg, _, e_seg = model.encode(seg)
-            d_seg = model.decode(c_seg, None)
-        np.savez_compressed(os.path.join(GOLD, "codec_demo2s.npz"), wav=seg.numpy(), weights_seed=3,
-                            codebook_mu=mu.numpy(), codebook_sigma=sigma.numpy(), ref_emb=e_seg.numpy(), ref_codes=c_seg.numpy(),
-                            ref_dec=d_seg.numpy(), full_len=data.shape[-1], full_frames=c_full.shape[-1])
+            wm_full, mlog_full = model.wmdecode(c_full, marks_full, data, None)
+        owm, omlog = oracle.wmdecode(c_full, marks_full, data)
+        print(f"[codec] demo wav wmdecode oracle vs reference: wav err {(owm - wm_full).abs().max().item():.3e} "
+              f"mark-logit err {(omlog - mlog_full).abs().max().item():.3e}")
+        np.savez_compressed(os.path.join(GOLD, "codec_demo.npz"), wav=data.numpy(), weights_seed=3,
+                            codebook_mu=mu.numpy(), codebook_sigma=sigma.numpy(), ref_emb=e_full.numpy(), ref_codes=c_full.numpy(),
+                            ref_dec=d_full.numpy(), marks=marks_full.numpy(), ref_wm=wm_full.numpy(),
+                            ref_mark_logits=mlog_full.numpy(), n_samples=int(data.shape[-1] - pad))
     except Exception as e:  # pragma: no cover
         print("[codec] demo wav case skipped:", repr(e))
     return rep

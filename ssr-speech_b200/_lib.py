@@ -47,7 +47,7 @@ EXPORTS = [
     "ssrb_lm_step_bytes", "ssrb_lm_profile_steps",
     "ssrb_codec_create", "ssrb_codec_destroy", "ssrb_codec_load_tensor", "ssrb_codec_check_loaded",
     "ssrb_codec_encode", "ssrb_codec_quantize", "ssrb_codec_decode", "ssrb_codec_wmdecode", "ssrb_codec_detect_watermark",
-    "ssrb_op_gemm", "ssrb_op_gemm_ln", "ssrb_op_layer_chain", "ssrb_debug_timeline",
+    "ssrb_op_gemm", "ssrb_op_gemm_ln", "ssrb_op_layer_chain", "ssrb_op_attn_decode", "ssrb_op_attn_prefill", "ssrb_debug_timeline",
 ]
 
 _lib = None
@@ -95,6 +95,8 @@ def load():
     lib.ssrb_op_gemm.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]
     lib.ssrb_op_gemm_ln.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp]
     lib.ssrb_op_layer_chain.argtypes = [vp] * 16 + [C.c_int] * 4 + [vp]
+    lib.ssrb_op_attn_decode.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]
+    lib.ssrb_op_attn_prefill.argtypes = [vp, vp, vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp]
     _lib = lib
     return lib
 

@@ -180,24 +180,51 @@ WMEncodecModel.detect_watermark = _detect_watermark
 
 
 def _cfg_from_xp(xp_cfg) -> CodecConfig:
-    """Best-effort read of the resolved Hydra cfg stored in the checkpoint (wmcompression.py:302-304)."""
-    def get(o, k, d=None):
+    """Reads the resolved Hydra cfg stored in the checkpoint (wmcompression.py:302-304; consumed by
+    models/builders.py:68-113: cfg.seanet -> SEANet kwargs, cfg.rvq -> quantizer, cfg.sample_rate / cfg.channels).
+    Strict: a missing section / key or a value these kernels do not implement raises instead of silently decoding with the
+    default geometry (other ratios or bins would produce garbage without a word)."""
+    def get(o, k, where):
         try:
-            return o[k] if k in o else d
-        except Exception:
-            return getattr(o, k, d)
-    cfg = CodecConfig()
+            if isinstance(o, dict) or hasattr(o, "keys"):
+                if k in o:
+                    return o[k]
+            elif hasattr(o, k):
+                return getattr(o, k)
+        except Exception as e:
+            raise ValueError(f"malformed xp.cfg: cannot read {where}.{k}: {e!r}") from e
+        raise ValueError(f"malformed xp.cfg: {where}.{k} is missing")
+
+    def opt(o, k, default):
+        try:
+            return get(o, k, "")
+        except ValueError:
+            return default
+    if xp_cfg is None:
+        raise ValueError("malformed checkpoint: 'xp.cfg' is None")
+    se, rv = get(xp_cfg, "seanet", "xp.cfg"), get(xp_cfg, "rvq", "xp.cfg")
     try:
-        se, rv = get(xp_cfg, "seanet", {}), get(xp_cfg, "rvq", {})
         cfg = CodecConfig(
-            channels=int(get(xp_cfg, "channels", 1)), dimension=int(get(se, "dimension", 128)),
-            n_filters=int(get(se, "n_filters", 64)), ratios=tuple(int(r) for r in get(se, "ratios", (8, 5, 4, 2))),
-            kernel_size=int(get(se, "kernel_size", 7)), residual_kernel_size=int(get(se, "residual_kernel_size", 3)),
-            last_kernel_size=int(get(se, "last_kernel_size", 7)), compress=int(get(se, "compress", 2)),
-            lstm=int(get(se, "lstm", 2)), n_q=int(get(rv, "n_q", 4)), bins=int(get(rv, "bins", 2048)),
-            sample_rate=int(get(xp_cfg, "sample_rate", 16000)))
-    except Exception:
-        pass
+            channels=int(get(xp_cfg, "channels", "xp.cfg")), dimension=int(get(se, "dimension", "xp.cfg.seanet")),
+            n_filters=int(get(se, "n_filters", "xp.cfg.seanet")),
+            ratios=tuple(int(r) for r in get(se, "ratios", "xp.cfg.seanet")),
+            kernel_size=int(get(se, "kernel_size", "xp.cfg.seanet")),
+            residual_kernel_size=int(get(se, "residual_kernel_size", "xp.cfg.seanet")),
+            last_kernel_size=int(get(se, "last_kernel_size", "xp.cfg.seanet")), compress=int(get(se, "compress", "xp.cfg.seanet")),
+            lstm=int(get(se, "lstm", "xp.cfg.seanet")), n_q=int(get(rv, "n_q", "xp.cfg.rvq")), bins=int(get(rv, "bins", "xp.cfg.rvq")),
+            sample_rate=int(get(xp_cfg, "sample_rate", "xp.cfg")))
+    except (TypeError, AttributeError) as e:
+        raise ValueError(f"malformed xp.cfg: {e!r}") from e
+    # what the kernels are specialised for (SURVEY Appendix A.2); present-and-different is an error, absent means default
+    fixed = {"n_residual_layers": 1, "activation": "ELU", "norm": "weight_norm", "dilation_base": 2, "pad_mode": "constant",
+             "true_skip": True, "causal": False, "disable_norm_outer_blocks": 0}
+    for k, want in fixed.items():
+        v = opt(se, k, want)
+        if v != want:
+            raise ValueError(f"xp.cfg.seanet.{k}={v!r} is not supported by the sm_100a codec kernels (need {want!r})")
+    enc = opt(xp_cfg, "encodec", None)
+    if enc is not None and bool(opt(enc, "renormalize", False)):
+        raise ValueError("xp.cfg.encodec.renormalize=True is not supported (the SSR-Speech codec uses renormalize=False)")
     return cfg
 
 

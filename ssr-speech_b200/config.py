@@ -86,6 +86,7 @@ class SSRConfig:
         assert self.head_dim == 128, "sm_100a attention kernels are specialised for head_dim=128"
         assert self.d_model % 128 == 0
         assert self.n_codebooks == 4, "sampling head is specialised for K=4 codebooks"
+        assert 1 <= self.max_n_spans <= 3, "the engine's per-utterance span state holds at most 3 spans (SSRB_MAX_SPANS)"
 
     def to_namespace(self) -> Namespace:
         """Namespace accepted by the reference's SSR_Speech(args) (for fixtures / checkpoints)."""

@@ -128,6 +128,9 @@ int ssrb_lm_create(const ssrb_lm_config* c, int device, ssrb_lm** out) {
     SSRB_CHECK(c->d_model % 128 == 0 && c->d_model / c->n_head == 128, "head_dim must be 128");
     SSRB_CHECK(c->d_model <= 2048, "d_model > 2048 not supported");
     SSRB_CHECK(c->n_codebooks == 4, "n_codebooks must be 4");
+    // UttState::span_len[] and ssrb_lm_read_tokens hold SSRB_MAX_SPANS entries: a checkpoint with more spans must fail here, not
+    // write past the array in sample_kernel
+    SSRB_CHECK(c->max_n_spans >= 1 && c->max_n_spans <= SSRB_MAX_SPANS, "max_n_spans must be 1..SSRB_MAX_SPANS (3)");
     SSRB_CHECK(c->weight_dtype == SSRB_DTYPE_F32 || c->weight_dtype == SSRB_DTYPE_BF16, "bad weight_dtype");
     SSRB_CHECK(c->max_rows > 0 && c->max_seq > 0 && c->max_prefill_tokens > 0 && c->max_steps > 0, "bad capacity");
     SSRB_CUDA(cudaSetDevice(device));
@@ -931,6 +934,68 @@ int ssrb_op_layer_chain(const void* ao, float* x_inout, const void* wo, const fl
     }
     cudaError_t ce = cudaStreamSynchronize(s);
     cudaFree(hn); cudaFree(w1f); cudaFree(wqf); cudaFree(c1); cudaFree(b1f); cudaFree(cq); cudaFree(bqf); cudaFree(part); cudaFree(gbar);
+    if (rc) return rc;
+    SSRB_CUDA(ce);
+    return 0;
+}
+
+// Decode attention exactly as the bf16 decode chain runs it (attn_decode_tma_kernel incl. the fused in-place KV append), on
+// caller-provided buffers.  Test hook for tests/test_gpu_attn_ops.py.
+int ssrb_op_attn_decode(const float* qkv, void* kcache, void* vcache, const int32_t* seq_len_host, const int32_t* done_host,
+                        void* out, int R, int D, int H, int Smax, void* stream) {
+    SSRB_CHECK(qkv && kcache && vcache && seq_len_host && out, "null argument");
+    SSRB_CHECK(R >= 1 && H >= 1 && D == H * 128 && Smax >= 1, "op_attn_decode: head_dim must be 128");
+    cudaStream_t s = (cudaStream_t)stream;
+    std::vector<UttState> st(R);
+    for (int r = 0; r < R; r++) {
+        SSRB_CHECK(seq_len_host[r] >= 0 && seq_len_host[r] < Smax, "op_attn_decode: seq_len must leave room for the appended row");
+        UttState z{}; z.done = done_host ? done_host[r] : 0; st[r] = z;
+    }
+    UttState* d_st = nullptr; int *d_seq = nullptr, *d_tk = nullptr; float* ws = nullptr;
+    SSRB_CUDA(cudaMalloc((void**)&d_st, R * sizeof(UttState))); SSRB_CUDA(cudaMalloc((void**)&d_seq, R * 4));
+    SSRB_CUDA(cudaMalloc((void**)&d_tk, (size_t)R * H * 4)); SSRB_CUDA(cudaMalloc((void**)&ws, attn_decode_ws_floats(R, H, Smax) * 4));
+    SSRB_CUDA(cudaMemcpyAsync(d_st, st.data(), R * sizeof(UttState), cudaMemcpyHostToDevice, s));
+    SSRB_CUDA(cudaMemcpyAsync(d_seq, seq_len_host, R * 4, cudaMemcpyHostToDevice, s));
+    SSRB_CUDA(cudaMemsetAsync(d_tk, 0, (size_t)R * H * 4, s));
+    int rc = launch_attn_decode(qkv, R, D, H, kcache, vcache, SSRB_DTYPE_BF16, Smax, d_seq, d_st, 1, ws, d_tk, out,
+                                SSRB_DTYPE_BF16, 0, s);
+    cudaError_t ce = cudaStreamSynchronize(s);
+    cudaFree(d_st); cudaFree(d_seq); cudaFree(d_tk); cudaFree(ws);
+    if (rc) return rc;
+    SSRB_CUDA(ce);
+    return 0;
+}
+
+// Prefill attention exactly as the bf16 prefill runs it: K/V of the packed positions are scattered into the cache
+// (kv_append_kernel), then attn_prefill_mma_kernel attends causally within each row.  Row i of the call uses cache row i.
+int ssrb_op_attn_prefill(const float* qkv, void* kcache, void* vcache, const int32_t* row_len_host, int n_rows, void* out,
+                         int D, int H, int Smax, void* stream) {
+    SSRB_CHECK(qkv && kcache && vcache && row_len_host && out && n_rows >= 1, "null argument");
+    SSRB_CHECK(H >= 1 && D == H * 128, "op_attn_prefill: head_dim must be 128");
+    cudaStream_t s = (cudaStream_t)stream;
+    std::vector<int> rows, slots, rid, rstart, rlen;
+    int M = 0, max_len = 0;
+    for (int i = 0; i < n_rows; i++) {
+        const int len = row_len_host[i];
+        SSRB_CHECK(len >= 1 && len <= Smax, "op_attn_prefill: bad row length");
+        rid.push_back(i); rstart.push_back(M); rlen.push_back(len);
+        for (int j = 0; j < len; j++) { rows.push_back(i); slots.push_back(j); }
+        M += len; if (len > max_len) max_len = len;
+    }
+    int *d_rows = nullptr, *d_slots = nullptr, *d_rid = nullptr, *d_rstart = nullptr, *d_rlen = nullptr;
+    SSRB_CUDA(cudaMalloc((void**)&d_rows, M * 4)); SSRB_CUDA(cudaMalloc((void**)&d_slots, M * 4));
+    SSRB_CUDA(cudaMalloc((void**)&d_rid, n_rows * 4)); SSRB_CUDA(cudaMalloc((void**)&d_rstart, n_rows * 4));
+    SSRB_CUDA(cudaMalloc((void**)&d_rlen, n_rows * 4));
+    SSRB_CUDA(cudaMemcpyAsync(d_rows, rows.data(), M * 4, cudaMemcpyHostToDevice, s));
+    SSRB_CUDA(cudaMemcpyAsync(d_slots, slots.data(), M * 4, cudaMemcpyHostToDevice, s));
+    SSRB_CUDA(cudaMemcpyAsync(d_rid, rid.data(), n_rows * 4, cudaMemcpyHostToDevice, s));
+    SSRB_CUDA(cudaMemcpyAsync(d_rstart, rstart.data(), n_rows * 4, cudaMemcpyHostToDevice, s));
+    SSRB_CUDA(cudaMemcpyAsync(d_rlen, rlen.data(), n_rows * 4, cudaMemcpyHostToDevice, s));
+    int rc = launch_kv_append(qkv, M, D, H, d_rows, d_slots, nullptr, kcache, vcache, SSRB_DTYPE_BF16, Smax, s);
+    if (!rc) rc = launch_attn_prefill(qkv, D, H, kcache, vcache, SSRB_DTYPE_BF16, Smax, n_rows, d_rid, d_rstart, d_rlen, max_len,
+                                      out, SSRB_DTYPE_BF16, s);
+    cudaError_t ce = cudaStreamSynchronize(s);
+    cudaFree(d_rows); cudaFree(d_slots); cudaFree(d_rid); cudaFree(d_rstart); cudaFree(d_rlen);
     if (rc) return rc;
     SSRB_CUDA(ce);
     return 0;

@@ -58,7 +58,7 @@ def encode_items(tokenizer: AudioTokenizer, items, save_root: str, batch_size: i
             if a.ndim > 1:
                 a = a.mean(0)
             audios.append(a)
-            durs.append(a.shape[0] / model_sr)
+            durs.append(a.shape[-1] / sr)      # as the reference: samples AFTER resampling over the ORIGINAL rate (data/encode.py:86)
             ids.append(it["segment_id"])
         padded = torch.nn.utils.rnn.pad_sequence(audios, batch_first=True).unsqueeze(1)        # [B,1,T]
         codes = tokenizer.encode(padded)[0].cpu()

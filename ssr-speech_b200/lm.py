@@ -123,9 +123,14 @@ class SSR_Speech:
         cap = self._cap
         if self._h is not None and cap[0] >= rows and cap[1] >= s0 and cap[2] >= prefill_tokens and cap[3] >= max_steps:
             return
-        if cap is not None:   # grow-only
-            rows, s0 = max(rows, cap[0]), max(s0, cap[1])
-            prefill_tokens, max_steps = max(prefill_tokens, cap[2]), max(max_steps, cap[3])
+        if cap is not None:
+            # grow-only, with headroom on the dimensions that outgrew the engine: a rebuild re-uploads every weight (3.3 GB for
+            # the 830M model), so a per-utterance loop over slowly growing requests (inference_v2.py:331-333) must not rebuild
+            # on every longer request.  The first build is exact; `reserve()` pre-sizes.
+            def grow(need, have):
+                return have if need <= have else max(need, (3 * have + 1) // 2)
+            rows, s0 = max(rows, cap[0]), grow(s0, cap[1])
+            prefill_tokens, max_steps = grow(prefill_tokens, cap[2]), grow(max_steps, cap[3])
         max_seq = s0 + max_steps + 8
         self._destroy()
         lib = _lib.load()
@@ -271,7 +276,9 @@ class SSR_Speech:
         batch = _lib.LMBatch(n_utt=U, text=text.ctypes.data_as(i32p), text_stride=Lmax, text_len=tl.ctypes.data_as(i32p),
                              prompt=prom.ctypes.data_as(i32p), prompt_stride=prom.shape[2],
                              prompt_len=pl.ctypes.data_as(i32p), n_spans=ns.ctypes.data_as(i32p))
-        sil = list(silence_tokens)[:_lib.MAX_SILENCE]
+        sil = [int(t) for t in silence_tokens]
+        if len(sil) > _lib.MAX_SILENCE:     # the reference accepts any list (ssr.py:727); truncating would change the sampling rule silently
+            raise ValueError(f"at most {_lib.MAX_SILENCE} silence tokens are supported, got {len(sil)}")
         if seed is None:
             seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item()) if noise is None else 0
         sp = _lib.Sampling(top_k=int(top_k), top_p=float(top_p), temperature=float(temperature),

@@ -78,11 +78,13 @@ def splice_original(wav: torch.Tensor, n_frames: int, masks, ori_masks, hop: int
 def inference_batch(model, audio_tokenizer: AudioTokenizer, wavs: List[torch.Tensor], text_ids: List[torch.Tensor],
                     mask_intervals: List, decode_config: Dict, cfg_coef: float = 1.5, cfg_stride: int = 5,
                     aug_text: bool = True, use_watermark: bool = True, tts: bool = True, seed: Optional[int] = None,
-                    timings: Optional[Dict[str, float]] = None):
+                    timings: Optional[Dict[str, float]] = None, to_host: bool = True):
     """Batched hot path with HOST inputs/outputs (this is what bench.py's `e2e` measures).
 
     wavs[i]: float32 [1, T_i] host tensors at 16 kHz (T_i multiple of 320, equal within the batch);
-    text_ids[i]: int64 [Lx_i]; mask_intervals[i]: [M_i, 2] frames.  Returns a list of host waveforms [1, T_out_i]."""
+    text_ids[i]: int64 [Lx_i]; mask_intervals[i]: [M_i, 2] frames.  Returns a list of host waveforms [1, T_out_i];
+    `to_host=False` leaves them in HBM (multi-GPU jobs gather on the device first and copy to the host once,
+    dist.gather_waveforms)."""
     dev = audio_tokenizer.device
     U = len(wavs)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
@@ -115,7 +117,7 @@ def inference_batch(model, audio_tokenizer: AudioTokenizer, wavs: List[torch.Ten
             gen = audio_tokenizer.wmdecode(fr, mk, nw.to(dev, non_blocking=True), scale)
         else:
             gen = audio_tokenizer.decode(fr, scale)
-        gen_h = gen.to("cpu")
+        gen_h = gen.to("cpu") if to_host else gen
         for j, i in enumerate(idxs):
             g = gen_h[j]
             if tts:

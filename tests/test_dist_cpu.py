@@ -26,6 +26,8 @@ def _worker(rank, world, port, n_items, q):
     local = [torch.full((1, 100 + 7 * i), float(i)) for i in range(lo, hi)]
     out = gather_waveforms(local, device=torch.device("cpu"))
     ok = len(out) == n_items and all(o.shape == (1, 100 + 7 * i) and bool((o == i).all()) for i, o in enumerate(out))
+    out_h = gather_waveforms(local, to_host=True)                  # default device (gloo: the tensors' own), one host copy
+    ok = ok and len(out_h) == n_items and all(torch.equal(a, b) for a, b in zip(out, out_h))
     q.put((rank, ok, lo, hi))
     dist.barrier()
     dist.destroy_process_group()
@@ -43,6 +45,20 @@ def test_shard_and_gather_world2():
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True, 0, 3), (1, True, 3, 5)]
+
+
+def test_shard_and_gather_world2_with_an_empty_shard():
+    """1 utterance over 2 ranks: rank 1 holds nothing and still takes part in both collectives."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, 1, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True, 0, 1), (1, True, 1, 1)]
 
 
 def test_gather_single_process_passthrough():

@@ -162,18 +162,44 @@ def test_reference_assertions(model_fp32):
 
 
 def test_sampling_distribution_top_p(model_fp32):
-    """Philox sampler statistics: with top_p the sampled ids stay inside the nucleus computed by the oracle filter."""
+    """In-kernel Philox sampler + radix-descent top-p threshold against the reference's filter (ssr.py:26-68, restated in
+    lm_oracle.filter_top_k_top_p): over 48 seeds the first sampled token of codebook 0 always lies inside the nucleus the
+    oracle computes from the engine's own raw logits (rules of ssr.py:698-723 applied first), the draws are not all the same
+    token, and the codebooks still inside the delay pattern emit the forced empty token."""
+    import ctypes as C
     from lm_oracle import filter_top_k_top_p
+    from ssr_speech_b200 import _lib
     cfg = cfg_tiny()
+    K = cfg.n_codebooks
     g = torch.Generator().manual_seed(3)
     x = torch.randint(0, cfg.text_vocab_size, (6,), generator=g)
     y = torch.randint(0, cfg.audio_vocab_size, (12, 4), generator=g)
-    seen = set()
-    for s in range(24):
-        model_fp32.inference_batch([x], [y], [[[12, 12]]], top_k=0, top_p=0.5, temperature=1.0, seed=s)
-        raw = model_fp32.last_raw_logits()
-        seen.add(s)
-    assert len(seen) == 24 and torch.isfinite(raw[0]).all()
+    lib = _lib.load()
+    seen, nucleus_sizes = set(), set()
+    for s in range(48):
+        model_fp32.open_batch([x], [y], [[[12, 12]]], top_k=0, top_p=0.5, temperature=1.0, seed=s)   # prefill + first sample
+        raw = model_fp32.last_raw_logits()[0].clone()                                                # [K, V] of iteration 1
+        buf = np.zeros((model_fp32._cap[3], K), dtype=np.int32)
+        sl, nt = (C.c_int32 * _lib.MAX_SPANS)(), C.c_int(0)
+        _lib.check(lib.ssrb_lm_read_tokens(model_fp32._h, _lib.stream_ptr(), 0, C.c_void_p(buf.ctypes.data), buf.shape[0],
+                                           C.byref(nt), sl), "read_tokens")
+        assert nt.value == 1
+        lg = raw.clone()
+        lg[:, cfg.eos] = -10000.0
+        lg[:, cfg.sos] = -10000.0
+        lg[:, cfg.mts:cfg.mts + cfg.max_n_spans] = -10000.0
+        lg[1:, cfg.empty_token] = 10000.0                 # num_gen = 0 < K - 1
+        lg[1:, cfg.eog] = -10000.0
+        keep = torch.isfinite(filter_top_k_top_p(lg, 0, 0.5))
+        tok0 = int(buf[0, 0])
+        if tok0 != cfg.eog:                               # eog may also be forced by argmax(logits[0]) == eog (ssr.py:739)
+            assert bool(keep[0, tok0]), (s, tok0)
+        assert 1 <= int(keep[0].sum()) < cfg.n_audio_tokens
+        assert all(int(buf[0, k]) == cfg.empty_token for k in range(1, K))
+        seen.add(tok0)
+        nucleus_sizes.add(int(keep[0].sum()))
+    assert len(seen) >= 3, seen                           # 48 draws from a nucleus of several tokens are not all equal
+    assert len(nucleus_sizes) == 1                        # same prompt -> same nucleus, only the draw changes
 
 
 def test_continuous_batching_equals_one_big_batch(model_fp32):
@@ -195,6 +221,29 @@ def test_continuous_batching_equals_one_big_batch(model_fp32):
     seq1 = model_fp32.serve(xs[:3], ys[:3], spans[:3], max_slots=1, uncond_xs=un[:3], **kw)
     for (r0, *_), (r1, *_) in zip(want[:3], seq1):
         assert torch.equal(r0.cpu(), r1.cpu())
+
+
+def test_continuous_batching_matches_oracle_greedy(model_fp32):
+    """serve() against the ORACLE (not against inference_batch): 6 ragged greedy requests with CFG rows (TTS, 1- and 2-span
+    edits) through 2 slots; every request must equal the oracle's independent roll-out token for token (greedy needs no
+    sampling noise, so admission order and slot reuse cannot hide behind the RNG)."""
+    cfg = cfg_tiny()
+    oracle = LMOracle(cfg, make_lm_state_dict(cfg, seed=7))
+    g = torch.Generator().manual_seed(23)
+    lens = [(5, 30), (7, 52), (4, 21), (6, 44), (5, 36), (8, 40)]
+    xs = [torch.randint(0, 100, (n,), generator=g) for n, _ in lens]
+    ys = [torch.randint(0, cfg.audio_vocab_size, (t, 4), generator=g) for _, t in lens]
+    spans = [[[30, 30]], [[10, 25]], [[21, 21]], [[3, 9], [20, 30]], [[0, 6]], [[40, 40]]]
+    un = [torch.randint(0, 101, (x.shape[0],), generator=g) for x in xs]
+    kw = dict(top_k=1, top_p=1.0, temperature=1.0, stop_repetition=-1, cfg_coef=1.5, cfg_stride=2, aug_text=True)
+    got = model_fp32.serve(xs, ys, spans, max_slots=2, uncond_xs=un, poll_every=3, seed=1, **kw)
+    for i in range(len(xs)):
+        prep = seq.prepare(cfg, ys[i].numpy().T.copy(), spans[i])
+        sp = oracle.inference(xs[i], torch.from_numpy(prep.prompt_tokens), prep.num_spans, uncond_x=un[i], **kw)
+        want, wmarks, wmasks, wnmi = seq.finalize(cfg, prep, sp)
+        res, marks, masks, nmi = got[i]
+        assert np.array_equal(res[0].cpu().numpy(), want), i
+        assert np.array_equal(marks[0].numpy(), wmarks) and list(masks) == list(wmasks) and list(nmi) == list(wnmi)
 
 
 def test_continuous_batching_bf16_runs(model_bf16):

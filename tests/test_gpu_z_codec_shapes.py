@@ -1,9 +1,7 @@
 """CUDA WM-Encodec kernels (fp32 parity mode, through the C ABI) against the oracle on the shapes of
 tests/test_codec_oracle_vs_reference_sweep.py — a single frame, odd frame counts, batch 3, all watermark patterns, silence — where
 the oracle itself is pinned against the unmodified reference in the build container.  Tolerances as in test_gpu_codec.py
-(SURVEY §8c item 4).
-
-Written after the round's last GPU run: gated by SSRB_EXPERIMENTAL=1 until it has been seen green on a B200 (then the gate goes)."""
+(SURVEY §8c item 4)."""
 import os
 
 import numpy as np
@@ -14,9 +12,7 @@ from codec_oracle import CodecOracle
 from test_codec_oracle_vs_reference_sweep import CASES, signals
 from test_gpu_codec import load, near_tie_only
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("SSRB_EXPERIMENTAL") != "1",
-                                 reason="recorded after the last GPU run of the round (set SSRB_EXPERIMENTAL=1)")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(scope="module")

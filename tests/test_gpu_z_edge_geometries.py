@@ -1,9 +1,7 @@
 """CUDA decode path (fp32 parity mode, through the C ABI) against the oracle on the span geometries of
 tests/test_oracle_vs_reference_sweep.py — spans at frame 0, at the last frame, adjacent, empty, whole-utterance, 1-3 spans —
 where the oracle itself is pinned against the unmodified reference in the build container.  Explicit Exp(1) noise makes the
-sampled cases exact.
-
-Written after the round's last GPU run: gated by SSRB_EXPERIMENTAL=1 until it has been seen green on a B200 (then the gate goes)."""
+sampled cases exact."""
 import os
 
 import numpy as np
@@ -17,9 +15,7 @@ from ssr_speech_b200.synth import make_lm_state_dict
 from test_gpu_lm import make_model
 from test_oracle_vs_reference_sweep import GREEDY, SAMPLED_CFG, SILENCE, edge_spans, random_spans
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("SSRB_EXPERIMENTAL") != "1",
-                                 reason="recorded after the last GPU run of the round (set SSRB_EXPERIMENTAL=1)")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(scope="module")

@@ -147,3 +147,91 @@ def test_decode_chunk_schedule_stops_at_the_iteration_bound():
     assert it == 505 and chunks[:-1] == [16] * 31 and chunks[-1] == 8
     assert SSR_Speech._next_chunk(16, 505, 505) == 1 and SSR_Speech._next_chunk(16, 10, 400) == 1     # past the bound: keep stepping
     assert SSR_Speech._next_chunk(1, 505, 3) == 1
+
+
+def _xp_cfg(**over):
+    """A resolved cfg shaped like the one audiocraft stores in the checkpoint (config/model/encodec/default.yaml +
+    encodec_large_nq4_s320.yaml), as plain dicts (OmegaConf is absent in this image; DictConfig answers `in` / [] alike)."""
+    cfg = {"sample_rate": 16000, "channels": 1, "compression_model": "wmencodec",
+           "encodec": {"autoencoder": "seanet", "quantizer": "rvq", "sample_rate": 16000, "channels": 1, "causal": False,
+                       "renormalize": False},
+           "seanet": {"dimension": 128, "channels": 1, "causal": False, "n_filters": 64, "n_residual_layers": 1,
+                      "ratios": [8, 5, 4, 2], "activation": "ELU", "activation_params": {"alpha": 1.0}, "norm": "weight_norm",
+                      "norm_params": {}, "kernel_size": 7, "residual_kernel_size": 3, "last_kernel_size": 7, "dilation_base": 2,
+                      "pad_mode": "constant", "true_skip": True, "compress": 2, "lstm": 2, "disable_norm_outer_blocks": 0},
+           "rvq": {"n_q": 4, "bins": 2048, "q_dropout": False}}
+    for k, v in over.items():
+        sec, _, key = k.partition("__")
+        if key:
+            if v is None:
+                cfg[sec].pop(key)
+            else:
+                cfg[sec][key] = v
+        elif v is None:
+            cfg.pop(sec)
+        else:
+            cfg[sec] = v
+    return cfg
+
+
+def test_codec_checkpoint_cfg_is_read_strictly():
+    """wmcompression.py:281-315: the checkpoint's 'xp.cfg' decides the codec geometry.  A good cfg is mirrored; a malformed or
+    unsupported one raises (it used to fall back to the default geometry silently)."""
+    from ssr_speech_b200.codec import _cfg_from_xp
+    assert _cfg_from_xp(_xp_cfg()) == CodecConfig()
+    c = _cfg_from_xp(_xp_cfg(seanet__ratios=[8, 5, 4, 4], rvq__bins=1024, seanet__n_filters=32))
+    assert c.ratios == (8, 5, 4, 4) and c.bins == 1024 and c.n_filters == 32 and c.hop_length == 640
+    c = _cfg_from_xp(Namespace(**{k: (Namespace(**v) if isinstance(v, dict) and k in ("seanet", "rvq", "encodec") else v)
+                                  for k, v in _xp_cfg().items()}))          # attribute-style access works too
+    assert c == CodecConfig()
+    for bad in (dict(seanet=None), dict(rvq__bins=None), dict(seanet__ratios=None), dict(seanet__causal=True),
+                dict(seanet__norm="none"), dict(seanet__n_residual_layers=3), dict(encodec__renormalize=True),
+                dict(seanet__ratios="8-5-4-2"), dict(sample_rate=None)):
+        with pytest.raises(ValueError):
+            _cfg_from_xp(_xp_cfg(**bad))
+    with pytest.raises(ValueError):
+        _cfg_from_xp(None)
+
+
+def test_audio_tokenizer_loads_a_reference_style_checkpoint(tmp_path):
+    """AudioTokenizer(signature=path) (data/tokenizer.py:99-113 -> wmcompression.py:281-315): {'xp.cfg', 'best_state': {'model'}}
+    is loaded, the cfg read, the state dict kept for the engine (no CUDA call until the first encode / decode)."""
+    from ssr_speech_b200.codec import AudioTokenizer
+    from ssr_speech_b200.synth import make_codec_state_dict
+    ccfg = CodecConfig(n_filters=8, ratios=(4, 2), bins=32)
+    sd = make_codec_state_dict(ccfg, seed=1)
+    path = tmp_path / "wmencodec.th"
+    torch.save({"xp.cfg": _xp_cfg(seanet__n_filters=8, seanet__ratios=[4, 2], rvq__bins=32), "best_state": {"model": sd},
+                "version": "test", "exported": True}, path)
+    tok = AudioTokenizer(signature=str(path), device="cuda:0")
+    assert tok.sample_rate == 16000 and tok.channels == 1 and tok.device == torch.device("cuda:0")
+    assert tok.codec.cfg == ccfg and tok.codec.cfg.hop_length == 8
+    assert set(tok.codec.state_dict()) == set(sd)
+    torch.save({"xp.cfg": _xp_cfg(seanet=None), "best_state": {"model": sd}}, path)
+    with pytest.raises(ValueError):
+        AudioTokenizer(signature=str(path), device="cuda:0")
+    torch.save({"best_state": {"model": sd}}, path)
+    with pytest.raises(AssertionError):
+        AudioTokenizer(signature=str(path), device="cuda:0")
+
+
+def test_silence_token_list_longer_than_the_engine_table_raises():
+    """ssr.py:727 accepts any list; the engine's table holds 8 — a longer list must fail loudly, not be truncated."""
+    from ssr_speech_b200.lm import SSR_Speech
+    from ssr_speech_b200.synth import make_lm_state_dict
+    cfg = cfg_tiny()
+    m = SSR_Speech(cfg.to_namespace(), precision="fp32")
+    m.load_state_dict(make_lm_state_dict(cfg, seed=7))
+    m._device = torch.device("cuda", 0)
+    m._ensure_engine = lambda *a, **k: None          # host-side argument handling only: no engine, no CUDA
+    x = torch.zeros(5, dtype=torch.long)
+    y = torch.zeros(10, 4, dtype=torch.long)
+    with pytest.raises(ValueError, match="silence"):
+        m.open_batch([x], [y], [[[10, 10]]], silence_tokens=list(range(9)))
+
+
+def test_max_n_spans_beyond_the_engine_state_is_rejected():
+    ns = cfg_tiny().to_namespace()
+    ns.max_n_spans = 4
+    with pytest.raises(AssertionError):
+        SSRConfig.from_args(ns)

@@ -92,16 +92,21 @@ def test_codec_oracle_decode_and_wmdecode(codec_oracle):
 
 
 def test_codec_oracle_demo_wav_roundtrip(gold_dir):
-    """BASELINE config 1 (first 2 s of demo/84_121550_000074_000000.wav): encode -> RVQ -> decode."""
-    g = np.load(os.path.join(gold_dir, "codec_demo2s.npz"))
+    """BASELINE configs[0]: the WHOLE demo/84_121550_000074_000000.wav (126 880 samples -> 127 040 -> 397 frames):
+    encode -> RVQ -> decode, and wmdecode with marks[100:200] = 1 (wmencodec.py:324-375), against the unmodified reference."""
+    g = np.load(os.path.join(gold_dir, "codec_demo.npz"))
     cfg = CodecConfig()
     sd = make_codec_state_dict(cfg, seed=int(g["weights_seed"]), codebook_mu=g["codebook_mu"], codebook_sigma=g["codebook_sigma"])
     o = CodecOracle(cfg, sd)
+    assert g["wav"].shape == (1, 1, 127040) and int(g["n_samples"]) == 126880
     codes, _, emb = o.encode(torch.from_numpy(g["wav"]))
-    assert codes.shape == (1, 4, 100)
+    assert codes.shape == (1, 4, 397)
     np.testing.assert_allclose(emb.numpy(), g["ref_emb"], atol=1e-6)
     assert np.array_equal(codes.numpy(), g["ref_codes"])
     np.testing.assert_allclose(o.decode(codes).numpy(), g["ref_dec"], atol=1e-6)
+    wm, ml = o.wmdecode(codes, torch.from_numpy(g["marks"]), torch.from_numpy(g["wav"]))
+    np.testing.assert_allclose(wm.numpy(), g["ref_wm"], atol=2e-6)
+    np.testing.assert_allclose(ml.numpy(), g["ref_mark_logits"], atol=2e-6)
 
 
 @pytest.mark.parametrize("name", ["tts_rep_greedy", "tts_rep_cfg_lowtemp", "tts_rep_cfg_greedy"])
