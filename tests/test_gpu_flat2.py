@@ -20,7 +20,8 @@ import ctypes as C, os, sys
 sys.path.insert(0, os.getcwd())
 import numpy as np, torch
 from ssr_speech_b200 import _lib
-M, N, K, act, with_res, out_bf16, out = (int(v) for v in sys.argv[1:7]) + (sys.argv[7],)
+M, N, K, act, with_res, out_bf16 = (int(v) for v in sys.argv[1:7])
+out = sys.argv[7]
 lib = _lib.load()
 g = torch.Generator(device="cuda").manual_seed(M * 13 + N + K)
 A = torch.randn(M, K, device="cuda", generator=g).bfloat16()

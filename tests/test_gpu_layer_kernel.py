@@ -76,7 +76,14 @@ def test_layer_kernel_matches_per_gemm_chain(case, tmp_path):
     ref = _run_op(case, 0, str(tmp_path / "ref.npz"))
     got = _run_op(case, 1, str(tmp_path / "got.npz"))
     assert np.isfinite(got["x"]).all() and np.isfinite(got["hid"]).all() and np.isfinite(got["qkv"]).all()
-    assert np.array_equal(got["x"], ref["x"]), float(np.abs(got["x"] - ref["x"]).max())
+    if case[1] == 2048:
+        # d_model 2048 (the production shape): the per-GEMM chain picks the same 8-way / 4-way split-K slices, so the
+        # residual stream (adds only, fixed order) is bit-identical
+        assert np.array_equal(got["x"], ref["x"]), float(np.abs(got["x"] - ref["x"]).max())
+    else:
+        # other widths: gemm_dec_kernel chooses its split-K factor from the k-block count (e.g. 4-way at d_model 512), the layer
+        # kernel always splits 8 / 4 ways -> same products, different fp32 summation order (seen on hardware: 9.5e-7 on |x| ~ 4)
+        assert float(np.abs(got["x"] - ref["x"]).max()) <= 2e-6 * max(1.0, float(np.abs(ref["x"]).max()))
     for k in ("hid", "qkv"):
         tol = 1e-5 * max(1.0, float(np.abs(ref[k]).max()))
         if k == "hid":

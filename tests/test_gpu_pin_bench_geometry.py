@@ -122,9 +122,11 @@ def test_ragged_cfg_rollout_logits_along_the_decode_chain(sd830, oracle830):
                     n_cmp_with_finished_peers += int(flags.sum() > 0)
     assert n_cmp >= 30 and n_cmp_with_finished_peers >= 6, (n_cmp, n_cmp_with_finished_peers)
     # the whole batch ends where the reference's length guard puts it (ssr.py:739): 10 * Lx - Y0 + 1 new frames + EOG drain
+    n_max = max(seq.expected_steps(cfg, lx[u], tt[u] + 10 - 1) for u in range(U))     # 585: Lx 101 with the 420-frame prompt
+    _lib.check(lib.ssrb_lm_decode(m._h, n_max - it.value, st), "decode")
     _lib.check(lib.ssrb_lm_poll(m._h, st, C.byref(nd), C.byref(it)), "poll")
-    assert nd.value == U
-    for u in (0, 5, 31):
+    assert nd.value == U and it.value == n_max
+    for u in range(U):
         res = m._collect(u, preps[u])[0]
         assert res.shape[-1] == tt[u] + 10 * lx[u] - (tt[u] + 10) + 1
 
