@@ -333,7 +333,9 @@ int launch_attn_decode_tma(const float* qkv, int R, int D, int H, void* kcache, 
         SSRB_CUDA(cudaFuncSetAttribute(attn_decode_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
     }
     SSRB_CHECK(R <= AT_MAXR, "attn_decode: too many rows for one launch");
-    return launch_pdl(attn_decode_tma_kernel, dim3(2 * n_sm), dim3(AT_THREADS), AT_SMEM, s, 1, qkv, D, H, (bf16*)kcache, (bf16*)vcache, Smax,
+    // SSRB_ATTN_CTAS_PER_SM=1: one persistent CTA per SM instead of two (leaves room for another stream's GEMM CTAs; probe switch)
+    static const int per_sm = [] { const char* e = getenv("SSRB_ATTN_CTAS_PER_SM"); return (e && e[0] == '1') ? 1 : 2; }();
+    return launch_pdl(attn_decode_tma_kernel, dim3(per_sm * n_sm), dim3(AT_THREADS), AT_SMEM, s, 1, qkv, D, H, (bf16*)kcache, (bf16*)vcache, Smax,
                       seq_len, st, rpu, ws, tickets, (bf16*)out, R, attn_decode_tma_max_nsplit(Smax), prefetch);
 }
 

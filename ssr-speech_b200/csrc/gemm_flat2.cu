@@ -1,6 +1,7 @@
-// gemm_flat2.cu — EXPERIMENTAL prefill GEMM on CTA pairs (tcgen05.mma.cta_group::2), off by default: SSRB_FLAT_2CTA=1.
-// sm_100a only.  NOT yet run on hardware (written after this round's GPU budget was spent); gemm_flat_kernel (gemm_tc.cu) stays
-// the product path until tests/test_gpu_flat2.py is green on a B200.
+// gemm_flat2.cu — prefill GEMM on CTA pairs (tcgen05.mma.cta_group::2).  Default path for M > 128 since round 2: verified on a B200
+// (tests/test_gpu_flat2.py: 10 shapes vs torch fp32 and vs the 1-CTA kernel, whole roll-outs) and measured: prefill of the bench
+// batch 92.3 -> 78.8 ms (profiles/r02a_summary.md).  SSRB_FLAT_2CTA=0 selects the 1-CTA gemm_flat_kernel of gemm_tc.cu.
+// sm_100a only.
 //
 //   C[M,N] = act(A[M,K] . W[N,K]^T + bias) (+ residual)         A, W bf16 K-major; fp32 accumulate; M > 128 (prefill)
 //
@@ -245,7 +246,7 @@ __global__ void __launch_bounds__(192, 1) gemm_flat2_kernel(const __grid_constan
 }  // namespace
 
 bool gemm_flat2_enabled() {
-    static const bool on = [] { const char* e = getenv("SSRB_FLAT_2CTA"); return e && e[0] == '1'; }();
+    static const bool on = [] { const char* e = getenv("SSRB_FLAT_2CTA"); return !(e && e[0] == '0'); }();     // default on since round 2 (SSRB_FLAT_2CTA=0: the 1-CTA gemm_flat_kernel)
     return on;
 }
 

@@ -1000,7 +1000,7 @@ int gemm_tc(const GemmArgs& g, void*, size_t, cudaStream_t s) {
             default: return launch_tc<128, true>(maps, prm, grid, s);
         }
     }
-    if (gemm_flat2_enabled() && gemm_flat2_supported(g)) return gemm_flat2(g, s);     // experimental CTA-pair kernel (gemm_flat2.cu)
+    if (gemm_flat2_enabled() && gemm_flat2_supported(g)) return gemm_flat2(g, s);     // CTA-pair kernel (gemm_flat2.cu), default
     prm.splits = 1; prm.kb_per_split = prm.nkb;
     static const bool flat_old = [] { const char* e = getenv("SSRB_FLAT_OLD"); return e && e[0] == '1'; }();
     const bool vec_ok = g.N % 4 == 0 && g.ldc % 8 == 0 && (!g.residual || g.ldr % 4 == 0) &&

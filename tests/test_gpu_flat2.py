@@ -1,7 +1,6 @@
-"""EXPERIMENTAL — the CTA-pair prefill GEMM (csrc/gemm_flat2.cu, tcgen05.mma.cta_group::2, SSRB_FLAT_2CTA=1) against torch fp32
-and against the 1-CTA kernel it would replace.  Written after round 1's GPU budget was spent: skipped unless
-SSRB_EXPERIMENTAL=1; gemm_flat_kernel stays the product path until this file is green on a B200.  Every case runs in a child
-process under a timeout (the kernel's spins trap after 2 s, a hang would otherwise cost the box)."""
+"""The CTA-pair prefill GEMM (csrc/gemm_flat2.cu, tcgen05.mma.cta_group::2; the default prefill GEMM since round 2) against torch
+fp32 and against the 1-CTA kernel it replaced (SSRB_FLAT_2CTA=0).  Every case runs in a child process under a timeout (the
+kernel's spins trap after 2 s, a hang would otherwise cost the box)."""
 import os
 import subprocess
 import sys
@@ -11,9 +10,7 @@ import pytest
 
 from conftest import ROOT
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("SSRB_EXPERIMENTAL") != "1",
-                                 reason="experimental kernel, not yet verified on hardware (set SSRB_EXPERIMENTAL=1)")]
+pytestmark = pytest.mark.gpu
 
 SNIPPET = r"""
 import ctypes as C, os, sys
