@@ -129,6 +129,11 @@ int ssrb_lm_poll_flags(ssrb_lm* lm, void* stream, int32_t* done_flags, int* n_it
  * span.  Capacity `cap` iterations.  Synchronises. */
 int ssrb_lm_read_tokens(ssrb_lm* lm, void* stream, int utt, int32_t* out, int cap, int* n_tokens, int32_t* span_len);
 
+/* Which kernels the decode iterations of the open batch run through (test / bench introspection): 0 = per-GEMM chain with separate
+ * LayerNorm kernels (fp32 parity mode, SIMT), 1 = per-GEMM chain with folded LayerNorm (bf16, rows <= 128), 2 = experimental
+ * per-layer kernel, 3 = the persistent whole-iteration kernel for <= 16 rows (csrc/lm_mega.cu); -1 = no open batch. */
+int ssrb_lm_decode_path(ssrb_lm* lm);
+
 /* Test hook: raw head outputs of the most recent iteration, fp32 [n_rows, n_codebooks, n_audio_tokens]
  * (the tensor `logits` of ssr.py:688 before CFG / rules).  Synchronises. */
 int ssrb_lm_read_logits(ssrb_lm* lm, void* stream, float* host_out);
@@ -196,6 +201,12 @@ int ssrb_codec_detect_watermark(ssrb_codec* c, const float* wav_dev, int B, int 
 /* Debug: arms (dev_buf != NULL) or disarms the in-kernel timeline of the decode-chain kernels.  dev_buf holds cap x 4 u64
  * records {kernel id, CTA id, globaltimer ns at entry, at exit}; *dev_idx counts records (tools/timeline.py). */
 int ssrb_debug_timeline(unsigned long long* dev_buf, unsigned int* dev_idx, unsigned int cap);
+
+/* Debug: arms (dev_buf != NULL) or disarms the per-CTA trace of the persistent small-batch decode kernel (csrc/lm_mega.cu):
+ * consumer thread 0 of CTA c writes %globaltimer (ns) stamps into dev_buf[c * cap_per_cta ...] at kernel entry, dependency
+ * resolved, then per phase {start (grid barrier passed), activations staged, chunks consumed (GEMV phases only), end}.
+ * *n_ctas receives the kernel's grid size (tools/mega_trace.py). */
+int ssrb_debug_mega_trace(unsigned long long* dev_buf, int cap_per_cta, int* n_ctas);
 
 /* ------------------------------------------------------------------------------------------------
  * Stand-alone op hooks used by the unit tests (each runs exactly the kernel the engines use).

@@ -43,11 +43,11 @@ class CodecConfigC(C.Structure):
 EXPORTS = [
     "ssrb_last_error", "ssrb_version", "ssrb_launch_count",
     "ssrb_lm_create", "ssrb_lm_destroy", "ssrb_lm_load_tensor", "ssrb_lm_check_loaded", "ssrb_lm_begin",
-    "ssrb_lm_decode", "ssrb_lm_poll", "ssrb_lm_admit", "ssrb_lm_poll_flags", "ssrb_lm_read_tokens", "ssrb_lm_read_logits", "ssrb_lm_teacher_forced",
+    "ssrb_lm_decode", "ssrb_lm_poll", "ssrb_lm_admit", "ssrb_lm_poll_flags", "ssrb_lm_read_tokens", "ssrb_lm_read_logits", "ssrb_lm_decode_path", "ssrb_lm_teacher_forced",
     "ssrb_lm_step_bytes", "ssrb_lm_profile_steps",
     "ssrb_codec_create", "ssrb_codec_destroy", "ssrb_codec_load_tensor", "ssrb_codec_check_loaded",
     "ssrb_codec_encode", "ssrb_codec_quantize", "ssrb_codec_decode", "ssrb_codec_wmdecode", "ssrb_codec_detect_watermark",
-    "ssrb_op_gemm", "ssrb_op_gemm_ln", "ssrb_op_layer_chain", "ssrb_op_attn_decode", "ssrb_op_attn_prefill", "ssrb_debug_timeline",
+    "ssrb_op_gemm", "ssrb_op_gemm_ln", "ssrb_op_layer_chain", "ssrb_op_attn_decode", "ssrb_op_attn_prefill", "ssrb_debug_timeline", "ssrb_debug_mega_trace",
 ]
 
 _lib = None
@@ -78,6 +78,7 @@ def load():
     lib.ssrb_lm_poll_flags.argtypes = [vp, vp, vp, ip]
     lib.ssrb_lm_read_tokens.argtypes = [vp, vp, C.c_int, vp, C.c_int, ip, vp]
     lib.ssrb_lm_read_logits.argtypes = [vp, vp, vp]
+    lib.ssrb_lm_decode_path.argtypes = [vp]
     lib.ssrb_lm_teacher_forced.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, vp]
     lib.ssrb_lm_step_bytes.argtypes = [vp, vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.ssrb_lm_profile_steps.argtypes = [vp, C.c_int, vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
@@ -92,6 +93,7 @@ def load():
     lib.ssrb_codec_wmdecode.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp]
     lib.ssrb_codec_detect_watermark.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp]
     lib.ssrb_debug_timeline.argtypes = [vp, vp, C.c_uint]
+    lib.ssrb_debug_mega_trace.argtypes = [vp, C.c_int, ip]
     lib.ssrb_op_gemm.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]
     lib.ssrb_op_gemm_ln.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp]
     lib.ssrb_op_layer_chain.argtypes = [vp] * 16 + [C.c_int] * 4 + [vp]

@@ -35,6 +35,12 @@ static bool layer_kernel_enabled() {
     static const bool on = [] { const char* e = getenv("SSRB_LAYER_KERNEL"); return e && e[0] == '1'; }();
     return on;
 }
+// SSRB_MEGA=1 (experimental, default off): batches of <= 16 rows decode through the persistent whole-iteration kernel (lm_mega.cu)
+// instead of the per-GEMM chain.  Read at every engine creation (tests switch it inside one process).
+static bool mega_enabled() {
+    const char* e = getenv("SSRB_MEGA");
+    return e && e[0] == '1';
+}
 static bool attn_prefetch_enabled() {
     static const bool on = [] { const char* e = getenv("SSRB_ATTN_PREFETCH"); return !(e && e[0] == '0'); }();
     return on;
@@ -79,6 +85,13 @@ struct ssrb_lm {
     bool fold = false;         // the open batch decodes through the folded chain (R <= 128)
     bool layer_kernel = false; // ... with the persistent per-layer GEMM kernel (gemm_layer.cu)
     unsigned int* gbar = nullptr;   // its grid barrier {count, generation}
+    // persistent whole-iteration kernel for R <= 16 rows (lm_mega.cu): weights re-packed into streaming order on first use
+    bool mega_ok = false;      // configuration supports it (bf16, shapes) and SSRB_MEGA != 0
+    bool mega = false;         // the open batch decodes through it
+    bool mega_dirty = true;    // weights changed since the packed copies were built
+    std::vector<void*> mega_w; // packed matrices: 4 per layer + 2 heads
+    void* mega_layers = nullptr;    // device array of per-layer records
+    unsigned int* mega_bar = nullptr;
     float2* ln_part = nullptr; // [max_rows][d_model / 128] {mean, M2} partials of the residual stream
     std::map<std::string, bool> loaded;
     // workspace
@@ -200,6 +213,10 @@ int ssrb_lm_create(const ssrb_lm_config* c, int device, ssrb_lm** out) {
     SSRB_TRY(dev_alloc((void**)&lm->d_iter, 4));
     SSRB_TRY(dev_alloc((void**)&lm->gbar, 64 * 4));
     SSRB_CUDA(cudaMemset(lm->gbar, 0, 64 * 4));
+    SSRB_TRY(dev_alloc((void**)&lm->mega_bar, 64 * 4));
+    SSRB_CUDA(cudaMemset(lm->mega_bar, 0, 64 * 4));
+    lm->mega_ok = mega_enabled() && c->weight_dtype == SSRB_DTYPE_BF16 && c->gemm_impl != 1 &&
+                  mega_supported(1, D, lm->H, F, K, V, Hh);
     guard.p = nullptr;
     *out = lm;
     return 0;
@@ -219,8 +236,9 @@ void ssrb_lm_destroy(ssrb_lm* lm) {
                   lm->qkv, lm->logits, lm->hn, lm->ao, lm->hid, lm->hlast, lm->hh, lm->kcache, lm->vcache, lm->attn_ws,
                   lm->tickets, lm->tc_ws, lm->d_desc, lm->d_rows, lm->d_slots, lm->d_row_ids, lm->d_row_start,
                   lm->d_row_len, lm->d_last_idx, lm->d_state, lm->d_seq_len, lm->d_next_tok, lm->d_gen_tok, lm->d_iter,
-                  lm->staging, lm->hw1_f, lm->hc1, lm->hb1_f, lm->ln_part, lm->gbar};
+                  lm->staging, lm->hw1_f, lm->hc1, lm->hb1_f, lm->ln_part, lm->gbar, lm->mega_layers, lm->mega_bar};
     for (void* p : ps) cudaFree(p);
+    for (void* p : lm->mega_w) cudaFree(p);
     delete lm;
 }
 
@@ -302,6 +320,7 @@ int ssrb_lm_load_tensor(ssrb_lm* lm, const char* name_c, const float* host, cons
     }
     lm->loaded[name] = true;
     lm->fold_dirty = true;
+    lm->mega_dirty = true;
     return 0;
 }
 
@@ -316,6 +335,44 @@ static int fold_weights(ssrb_lm* lm, cudaStream_t s) {
     SSRB_TRY(launch_fold_ln(lm->hw1, lm->K * lm->Hh, D, lm->lnfw, lm->lnfb, lm->hb1, lm->hw1_f, lm->hc1, lm->hb1_f, s));
     SSRB_CUDA(cudaStreamSynchronize(s));
     lm->fold_dirty = false;
+    return 0;
+}
+
+// (re)build the streaming-order copies of every matrix the persistent small-batch kernel reads (lm_mega.cu), and its per-layer
+// records.  1.65 GB for the 830M model, allocated the first time a batch of <= 16 rows is opened.
+static int mega_prepare(ssrb_lm* lm, cudaStream_t s) {
+    if (!lm->mega_dirty && !lm->mega_w.empty()) return 0;
+    const int D = lm->D, F = lm->F, L = lm->L, K = lm->K, V = lm->V, Hh = lm->Hh;
+    const size_t e = 2;
+    if (lm->mega_w.empty()) {
+        lm->mega_w.assign((size_t)4 * L + 2, nullptr);
+        for (int n = 0; n < L; n++) {
+            SSRB_TRY(dev_alloc(&lm->mega_w[4 * n + 0], (size_t)3 * D * D * e)); SSRB_TRY(dev_alloc(&lm->mega_w[4 * n + 1], (size_t)D * D * e));
+            SSRB_TRY(dev_alloc(&lm->mega_w[4 * n + 2], (size_t)F * D * e)); SSRB_TRY(dev_alloc(&lm->mega_w[4 * n + 3], (size_t)D * F * e));
+        }
+        SSRB_TRY(dev_alloc(&lm->mega_w[4 * L], (size_t)K * Hh * D * e)); SSRB_TRY(dev_alloc(&lm->mega_w[4 * L + 1], (size_t)K * V * Hh * e));
+        SSRB_TRY(dev_alloc(&lm->mega_layers, (size_t)L * mega_layer_bytes()));
+    }
+    std::vector<char> recs((size_t)L * mega_layer_bytes());
+    for (int n = 0; n < L; n++) {
+        const LayerW& w = lm->layers[n];
+        SSRB_TRY(mega_pack(w.wqkv, lm->mega_w[4 * n + 0], 3 * D, D, MEGA_QKV, s));
+        SSRB_TRY(mega_pack(w.wo, lm->mega_w[4 * n + 1], D, D, MEGA_OUT, s));
+        SSRB_TRY(mega_pack(w.w1, lm->mega_w[4 * n + 2], F, D, MEGA_FFN1, s));
+        SSRB_TRY(mega_pack(w.w2, lm->mega_w[4 * n + 3], D, F, MEGA_FFN2, s));
+        MegaLayerHost h{};
+        h.D = D; h.F = F;
+        h.wqkv = lm->mega_w[4 * n + 0]; h.wo = lm->mega_w[4 * n + 1]; h.w1 = lm->mega_w[4 * n + 2]; h.w2 = lm->mega_w[4 * n + 3];
+        h.bqkv = w.bqkv; h.bo = w.bo; h.b1 = w.b1; h.b2 = w.b2; h.ln1g = w.ln1w; h.ln1b = w.ln1b; h.ln2g = w.ln2w; h.ln2b = w.ln2b;
+        h.kc = (char*)lm->kcache + (size_t)n * lm->kv_layer_elems * lm->esz;
+        h.vc = (char*)lm->vcache + (size_t)n * lm->kv_layer_elems * lm->esz;
+        SSRB_TRY(mega_fill_layer(recs.data() + (size_t)n * mega_layer_bytes(), h));
+    }
+    SSRB_TRY(mega_pack(lm->hw1, lm->mega_w[4 * L], K * Hh, D, MEGA_H1, s));
+    SSRB_TRY(mega_pack(lm->hw2, lm->mega_w[4 * L + 1], K * V, Hh, MEGA_H2, s));
+    SSRB_CUDA(cudaMemcpyAsync(lm->mega_layers, recs.data(), recs.size(), cudaMemcpyHostToDevice, s));
+    SSRB_CUDA(cudaStreamSynchronize(s));
+    lm->mega_dirty = false;
     return 0;
 }
 
@@ -463,7 +520,27 @@ static int run_heads(ssrb_lm* lm, const int* gather_idx, int M, void* hl, void* 
     return 0;
 }
 
+// a decode iteration of a small batch (R <= 16): embedding, ONE persistent kernel for the 16 layers and the heads, sampler
+static int enqueue_step_mega(ssrb_lm* lm, cudaStream_t s) {
+    { ProfScope ps(lm, PC_SMALL, s);
+      SSRB_TRY(launch_embed_step(lm->d_next_tok, lm->d_state, lm->R, lm->rpu, lm->K, lm->D, lm->audio_emb, lm->V, lm->pe,
+                                 lm->alpha_a, lm->x, s, lm->mega_bar)); }
+    { ProfScope ps(lm, PC_GEMM, s);
+      MegaArgs a{};
+      a.R = lm->R; a.D = lm->D; a.H = lm->H; a.F = lm->F; a.L = lm->L; a.NCB = lm->K; a.V = lm->V; a.Hh = lm->Hh;
+      a.Smax = lm->cfg.max_seq; a.rpu = lm->rpu; a.max_pieces = attn_decode_tma_max_nsplit(lm->cfg.max_seq);
+      a.x = lm->x; a.qkv = lm->qkv; a.ao = lm->ao; a.hid = lm->hid; a.hh = lm->hh; a.logits = lm->logits;
+      a.seq_len = lm->d_seq_len; a.st = lm->d_state; a.attn_ws = lm->attn_ws; a.tickets = lm->tickets; a.bar = lm->mega_bar;
+      a.layers_dev = lm->mega_layers;
+      a.h1_w = lm->mega_w[(size_t)4 * lm->L]; a.h2_w = lm->mega_w[(size_t)4 * lm->L + 1]; a.h1_b = lm->hb1; a.h2_b = lm->hb2;
+      a.lnf_g = lm->lnfw; a.lnf_b = lm->lnfb;
+      SSRB_TRY(launch_mega(a, s)); }
+    ProfScope ps(lm, PC_SAMPLE, s);
+    return launch_sample(lm->logits, lm->d_state, lm->d_seq_len, lm->d_next_tok, lm->d_gen_tok, lm->noise, lm->d_iter, lm->sp, s);
+}
+
 static int enqueue_step(ssrb_lm* lm, cudaStream_t s) {
+    if (lm->mega) return enqueue_step_mega(lm, s);
     if (lm->fold) {
         { ProfScope ps(lm, PC_SMALL, s);
           SSRB_TRY(launch_embed_step_fold(lm->d_next_tok, lm->d_state, lm->R, lm->rpu, lm->K, lm->D, lm->audio_emb, lm->V,
@@ -565,6 +642,8 @@ int ssrb_lm_begin(ssrb_lm* lm, const ssrb_lm_batch* b, const ssrb_sampling* sp, 
     lm->n_utt = U; lm->rpu = rpu; lm->R = R; lm->noise = noise_dev;
     SSRB_TRY(fold_weights(lm, s));
     lm->fold = lm->fold_ok && R <= 128;
+    lm->mega = lm->mega_ok && R <= 16 && mega_supported(R, lm->D, lm->H, lm->F, lm->K, lm->V, lm->Hh);
+    if (lm->mega) SSRB_TRY(mega_prepare(lm, s));
     lm->layer_kernel = lm->fold && layer_kernel_enabled() && gemm_layer_supported(R, lm->D, lm->F);
     if (lm->layer_kernel) SSRB_CUDA(cudaMemsetAsync(lm->gbar, 0, 64 * 4, s));   // a launch that died mid-barrier must not poison the next batch
     if (lm->graph) { cudaGraphExecDestroy(lm->graph); lm->graph = nullptr; }
@@ -738,6 +817,13 @@ int ssrb_lm_read_tokens(ssrb_lm* lm, void* stream, int utt, int32_t* out, int ca
     return 0;
 }
 
+int ssrb_lm_decode_path(ssrb_lm* lm) {
+    if (!lm || lm->R <= 0) return -1;
+    if (lm->mega) return 3;
+    if (lm->fold) return lm->layer_kernel ? 2 : 1;
+    return 0;
+}
+
 int ssrb_lm_read_logits(ssrb_lm* lm, void* stream, float* host_out) {
     SSRB_CHECK(lm && lm->R > 0 && host_out, "no active batch");
     cudaStream_t s = (cudaStream_t)stream;
@@ -833,6 +919,13 @@ int ssrb_debug_timeline(unsigned long long* dev_buf, unsigned int* dev_idx, unsi
     TsBuf t{dev_buf, dev_idx, cap};
     SSRB_CHECK(!ts_arm_gemm_tc(t) && !ts_arm_attn_tma(t) && !ts_arm_lm_kernels(t) && !ts_arm_gemm_layer(t) && !ts_arm_gemm_flat2(t), "cudaMemcpyToSymbol failed");
     return 0;
+}
+
+int ssrb_debug_mega_trace(unsigned long long* dev_buf, int cap_per_cta, int* n_ctas) {
+    int G = 0;
+    SSRB_TRY(mega_grid(&G));
+    if (n_ctas) *n_ctas = G;
+    return mega_trace_arm(dev_buf, dev_buf ? cap_per_cta : 0);
 }
 
 int ssrb_op_gemm(const void* A, const void* W, const float* bias, const float* residual, float* C, int M, int N, int K,

@@ -39,9 +39,11 @@ __global__ void __launch_bounds__(256) embed_prefill_kernel(const PosDesc* __res
 
 __global__ void __launch_bounds__(256) embed_step_kernel(const int* __restrict__ next_tok, const UttState* __restrict__ st,
                                                          int rpu, int K, int D, const float* __restrict__ audio_emb, int V,
-                                                         const float* __restrict__ pe, float alpha_a, float* __restrict__ x) {
+                                                         const float* __restrict__ pe, float alpha_a, float* __restrict__ x,
+                                                         unsigned int* __restrict__ zero_word) {
     const int ts = ts_begin(TSK_EMBED);
     pdl_wait();
+    if (zero_word && blockIdx.x == 0 && threadIdx.x == 0) *zero_word = 0u;   // grid-barrier counter of decode_mega_kernel (lm_mega.cu)
     // first kernel of a decode iteration: dependents are released only once the previous iteration (sampler included) has
     // completed, so kernels further down the chain may read the row state / cached K/V before their own griddepcontrol.wait
     pdl_launch_dependents();
@@ -152,9 +154,9 @@ int launch_embed_prefill(const PosDesc* desc, int M, int D, const float* text_em
     return 0;
 }
 int launch_embed_step(const int* next_tok, const UttState* st, int R, int rpu, int K, int D, const float* audio_emb,
-                      int V, const float* pe, float alpha_a, float* x, cudaStream_t s) {
+                      int V, const float* pe, float alpha_a, float* x, cudaStream_t s, unsigned int* zero_word) {
     SSRB_CHECK(K == 4, "embed_step: K must be 4");
-    SSRB_LAUNCH_PDL(embed_step_kernel, R, 256, 0, s, next_tok, st, rpu, K, D, audio_emb, V, pe, alpha_a, x);
+    SSRB_LAUNCH_PDL(embed_step_kernel, R, 256, 0, s, next_tok, st, rpu, K, D, audio_emb, V, pe, alpha_a, x, zero_word);
     return 0;
 }
 

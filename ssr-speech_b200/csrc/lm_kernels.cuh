@@ -36,8 +36,9 @@ struct PosDesc { int text_tok; int a0, a1, a2, a3; int pe_idx; };   // text_tok 
 
 int launch_embed_prefill(const PosDesc* desc, int M, int D, const float* text_emb, const float* audio_emb, int V,
                          const float* pe, float alpha_t, float alpha_a, float* x, cudaStream_t s);
+// zero_word (optional): a device word the kernel clears — the grid-barrier counter of the persistent small-batch kernel
 int launch_embed_step(const int* next_tok, const UttState* st, int R, int rpu, int K, int D, const float* audio_emb,
-                      int V, const float* pe, float alpha_a, float* x, cudaStream_t s);
+                      int V, const float* pe, float alpha_a, float* x, cudaStream_t s, unsigned int* zero_word = nullptr);
 // decode step with LayerNorm folded into the GEMMs: also writes bf16(x) and the per-128-column {mean, M2} partials
 int launch_embed_step_fold(const int* next_tok, const UttState* st, int R, int rpu, int K, int D, const float* audio_emb,
                            int V, const float* pe, float alpha_a, float* x, void* xb, float2* part, int part_ld,
@@ -71,5 +72,28 @@ int launch_attn_prefill_mma(const float* qkv, int D, int H, const void* kcache, 
 // CFG + logit rules + top-k/top-p + sample + state machine (models/ssr.py:690-754)
 int launch_sample(const float* logits, UttState* st, int* seq_len, int* next_tok, int* gen_tok, const float* noise,
                   int* iter_counter, const SampleParams& p, cudaStream_t s, int only_utt = -1);
+
+// ---- persistent whole-iteration decode kernel for R <= 16 rows (lm_mega.cu) ------------------------------------------------
+struct MegaLayerHost {            // one decoder layer: PACKED bf16 weights (mega_pack), fp32 biases / LayerNorm parameters, cache
+    int D, F;
+    const void *wqkv, *wo, *w1, *w2;
+    const float *bqkv, *bo, *b1, *b2, *ln1g, *ln1b, *ln2g, *ln2b;
+    void *kc, *vc;
+};
+struct MegaArgs {
+    int R, D, H, F, L, NCB, V, Hh, Smax, rpu, max_pieces;
+    float* x; float* qkv; void* ao; void* hid; void* hh; float* logits;
+    const int* seq_len; const UttState* st; float* attn_ws; int* tickets; unsigned int* bar;
+    const void* layers_dev;       // device array of L records built with mega_fill_layer
+    const void *h1_w, *h2_w; const float *h1_b, *h2_b, *lnf_g, *lnf_b;
+};
+bool mega_supported(int R, int D, int H, int F, int NCB, int V, int Hh);
+enum { MEGA_QKV = 0, MEGA_OUT = 1, MEGA_FFN1 = 2, MEGA_FFN2 = 3, MEGA_H1 = 4, MEGA_H2 = 5 };
+int mega_pack(const void* W, void* out, int N, int K, int kind, cudaStream_t s);     // W [N, K] bf16 -> streaming order
+size_t mega_layer_bytes();
+int mega_fill_layer(void* host_slot, const MegaLayerHost& h);
+int launch_mega(const MegaArgs& a, cudaStream_t s);
+int mega_trace_arm(unsigned long long* dev_buf, int cap_per_cta);   // debug: per-CTA %globaltimer stamps (null disarms)
+int mega_grid(int* G_out);
 
 }  // namespace ssrb

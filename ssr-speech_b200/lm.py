@@ -453,6 +453,11 @@ class SSR_Speech:
             _lib.check(_lib.load().ssrb_lm_read_logits(self._h, _lib.stream_ptr(), C.c_void_p(out.ctypes.data)), "read_logits")
         return torch.from_numpy(out)
 
+    def decode_path(self) -> int:
+        """0 / 1 = per-GEMM chain (separate / folded LayerNorm), 2 = experimental per-layer kernel, 3 = persistent whole-iteration
+        kernel for <= 16 rows (ssrb_lm_decode_path); -1 without an open batch."""
+        return int(_lib.load().ssrb_lm_decode_path(self._h)) if self._h is not None else -1
+
     def step_bytes(self):
         wb, kb = C.c_double(0), C.c_double(0)
         with torch.cuda.device(self._device):
