@@ -18,7 +18,17 @@ import sys
 import types
 from argparse import Namespace
 
-REF_ROOT = os.environ.get("SSRB_REFERENCE_ROOT", "/root/reference")
+def _find_reference_root() -> str:
+    """SSRB_REFERENCE_ROOT, then /root/reference (build container), then <repo>/baseline/_ref (a checkout placed beside the repo,
+    git-ignored).  The reference is a script tree, not an installable package, so there is nothing to pip-install."""
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for cand in (os.environ.get("SSRB_REFERENCE_ROOT"), "/root/reference", os.path.join(here, "baseline", "_ref")):
+        if cand and os.path.isfile(os.path.join(cand, "models", "ssr.py")):
+            return cand
+    return os.environ.get("SSRB_REFERENCE_ROOT") or "/root/reference"
+
+
+REF_ROOT = _find_reference_root()
 
 
 def reference_available() -> bool:

@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libssr_b200.so")
-SOURCES = ["gemm_simt.cu", "gemm_tc.cu", "gemm_layer.cu", "gemm_flat2.cu", "lm_kernels.cu", "lm_mega.cu", "attn_decode_tma.cu", "attn_prefill_mma.cu", "lm_engine.cu", "codec_kernels.cu", "codec_cl.cu", "conv_tc.cu", "codec_engine.cu"]
+SOURCES = ["gemm_simt.cu", "gemm_tc.cu", "gemm_layer.cu", "gemm_flat2.cu", "lm_kernels.cu", "lm_mega.cu", "attn_decode_tma.cu", "attn_prefill_mma.cu", "lm_engine.cu", "codec_kernels.cu", "codec_cl.cu", "conv_tc.cu", "conv_tc32.cu", "resblock_tc.cu", "codec_engine.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--use_fast_math=false",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--expt-relaxed-constexpr"]
 

@@ -26,6 +26,9 @@ struct ConvW {
 // tensor-core operand of one convolution: W' [taps][N][Cw] bf16 (conv_tc.cu), fp32 bias (+ per-mark bias for wm_proj)
 struct TcW { bf16* w = nullptr; float* bias = nullptr; float* bias_alt = nullptr; int taps = 0, N = 0, Cw = 0, bias_mod = 0; };
 struct ClT { bf16* raw = nullptr; bf16* act = nullptr; int C = 0, T = 0; };   // channels-last tensor [B][G+T+G][C]
+// encoder path (conv_tc32.cu): fp32 channels-last; weights and ELU'd activations split into two TF32 numbers (hi, lo)
+struct Tc32W { float* wh = nullptr; float* wl = nullptr; float* bias = nullptr; int taps = 0, N = 0, Cw = 0; };
+struct Cl32 { float* raw = nullptr; float* hi = nullptr; float* lo = nullptr; int C = 0, T = 0; };
 struct LstmW {
     float *wih[4] = {}, *whh[4] = {}, *bsum[4] = {};
     bf16* wih_bf16[4] = {};            // tensor-core input projection (decoder-side LSTMs only)
@@ -56,6 +59,7 @@ struct ssrb_codec {
     unsigned int* bar = nullptr;
     Arena arena;
     std::map<std::string, TcW> tcw;
+    std::map<std::string, Tc32W> tc32w;
     std::vector<float> wm_embed_host;   // renormalised rows
     bool use_tc = false;
 };
@@ -92,6 +96,7 @@ void ssrb_codec_destroy(ssrb_codec* c) {
     for (auto& kv : c->convs) { cudaFree(kv.second.w); cudaFree(kv.second.b); cudaFree(kv.second.wt); }
     for (auto& kv : c->lstms) for (int l = 0; l < 4; l++) { cudaFree(kv.second.wih[l]); cudaFree(kv.second.whh[l]); cudaFree(kv.second.bsum[l]); }
     for (auto& kv : c->tcw) { cudaFree(kv.second.w); cudaFree(kv.second.bias); cudaFree(kv.second.bias_alt); }
+    for (auto& kv : c->tc32w) { cudaFree(kv.second.wh); cudaFree(kv.second.wl); cudaFree(kv.second.bias); }
     cudaFree(c->codebooks); cudaFree(c->cb_sq); cudaFree(c->wm_embed); cudaFree(c->bar); cudaFree(c->arena.base);
     delete c;
 }
@@ -494,6 +499,25 @@ static int conv_frame_tc(Ctx& x, const std::string& key, Tensor in, bool elu_in,
 }
 // SEANetResnetBlock on the tensor cores: y = x + conv_k1(ELU(conv_k3(ELU(x)))); only ELU(y) (and optionally y) is kept
 static int tc_resblock(Ctx& x, const std::string& prefix, const ClT& in, bool want_raw, ClT* out) {
+    static const bool unfused = [] { const char* e = getenv("SSRB_RESBLOCK_UNFUSED"); return e && e[0] == '1'; }();   // A/B switch: two conv_tc launches
+    if (!unfused && resblock_tc_supported(in.C) && in.raw && in.act) {
+        // depth-fused: one launch, the hidden activation stays in shared memory (resblock_tc.cu)
+        const TcW *W1, *W2;
+        SSRB_TRY(get_tcw(x.c, prefix + "block.1.conv.conv.", TC_CONV, 1, &W1));
+        SSRB_TRY(get_tcw(x.c, prefix + "block.3.conv.conv.", TC_CONV, 1, &W2));
+        SSRB_CHECK(W1->taps == 3 && W2->taps == 1, "fused resblock: kernel sizes must be 3 and 1");
+        const int G = CL_GUARD, C = in.C, T = in.T;
+        *out = cl_alloc(x, C, T, want_raw, true);
+        if (x.c->arena.dry) return 0;
+        ResblockTcArgs a;
+        a.B = x.B; a.T = T; a.C = C;
+        a.x_act = in.act; a.x_bstride = (long long)(T + 2 * G) * C; a.x_base_off = (long long)(G - 1) * C; a.rows_v = T + G + 1;
+        a.x_raw = in.raw; a.x_raw_off = (long long)G * C;
+        a.w1 = W1->w; a.w1_N = W1->N; a.w1_Cw = W1->Cw; a.b1 = W1->bias;
+        a.w2 = W2->w; a.w2_N = W2->N; a.w2_Cw = W2->Cw; a.b2 = W2->bias;
+        a.out_raw = out->raw; a.out_act = out->act; a.out_bstride = a.x_bstride; a.out_off = (long long)G * C;
+        return resblock_tc(a, x.s);
+    }
     ClT h;
     SSRB_TRY(tc_conv(x, prefix + "block.1.conv.conv.", TC_CONV, 1, in, in.act, nullptr, false, true, nullptr, 0, 1, &h));
     return tc_conv(x, prefix + "block.3.conv.conv.", TC_CONV, 1, h, h.act, in.raw, want_raw, true, nullptr, 0, 1, out);
@@ -553,6 +577,129 @@ static int skip_encoder_tc(Ctx& x, const std::string& p, const float* wav, int T
     return conv_frame_tc(x, p + "model.15.conv.conv.", b, true, nullptr, skip3);
 }
 
+// =====================================================================================================================
+// Encoder on the tensor cores at fp32-grade accuracy (cfg.tensor_cores, conv_tc32.cu): every convolution between the first
+// (1-channel) one and the LSTM as 3 x TF32 tap-GEMMs over channels-last fp32 activations.  The RVQ indices downstream must stay
+// reproducible, so nothing here is bf16.
+// =====================================================================================================================
+static inline float host_rna_tf32(float x) {                 // cvt.rna.tf32.f32: nearest, ties away from zero, low 13 bits cleared
+    unsigned int u; memcpy(&u, &x, 4);
+    if ((u & 0x7f800000u) == 0x7f800000u) return x;
+    u += 0x1000u; u &= 0xffffe000u;
+    float r; memcpy(&r, &u, 4);
+    return r;
+}
+static int get_tc32w(ssrb_codec* c, const std::string& key, int kind, int stride, const Tc32W** out) {
+    auto it = c->tc32w.find(key);
+    if (it != c->tc32w.end()) { *out = &it->second; return 0; }
+    const ConvW* W;
+    SSRB_TRY(get_conv(c, key, &W));
+    SSRB_CHECK(!W->hw.empty() && !W->hb.empty(), ("host weights missing for " + key).c_str());
+    Tc32W t;
+    std::vector<float> wp;
+    const int k = W->k, Cout = W->d0, Cin = W->d1;
+    SSRB_CHECK(Cout % 32 == 0, "tc32 repack: output channels must be a multiple of 32");
+    if (kind == TC_CONV) {                                   // W [Cout][Cin][k], stride 1: W'[q][n][ci]
+        SSRB_CHECK(Cin % 32 == 0, "tc32 repack: input channels must be a multiple of 32");
+        t.taps = k; t.N = Cout; t.Cw = Cin;
+        wp.assign((size_t)t.taps * t.N * t.Cw, 0.f);
+        for (int q = 0; q < k; q++)
+            for (int n = 0; n < Cout; n++)
+                for (int ci = 0; ci < Cin; ci++) wp[((size_t)q * t.N + n) * t.Cw + ci] = W->hw[((size_t)n * Cin + ci) * k + q];
+    } else {                                                 // TC_CONVS: W [Cout][Cin][2s] -> W'[q][n][r * Cin + ci] = W[n][ci][q * s + r]
+        const int s = stride;
+        SSRB_CHECK(k == 2 * s && (s * Cin) % 32 == 0, "tc32 strided conv repack: unsupported shape");
+        t.taps = 2; t.N = Cout; t.Cw = s * Cin;
+        wp.assign((size_t)t.taps * t.N * t.Cw, 0.f);
+        for (int q = 0; q < 2; q++)
+            for (int n = 0; n < Cout; n++)
+                for (int r = 0; r < s; r++)
+                    for (int ci = 0; ci < Cin; ci++) wp[((size_t)q * t.N + n) * t.Cw + r * Cin + ci] = W->hw[((size_t)n * Cin + ci) * k + q * s + r];
+    }
+    std::vector<float> hi(wp.size()), lo(wp.size());
+    for (size_t i = 0; i < wp.size(); i++) { hi[i] = host_rna_tf32(wp[i]); lo[i] = host_rna_tf32(wp[i] - hi[i]); }
+    SSRB_TRY(upload_new(&t.wh, hi.data(), hi.size()));
+    SSRB_TRY(upload_new(&t.wl, lo.data(), lo.size()));
+    SSRB_TRY(upload_new(&t.bias, W->hb.data(), W->hb.size()));
+    c->tc32w[key] = t;
+    *out = &c->tc32w[key];
+    return 0;
+}
+static Cl32 cl32_alloc(Ctx& x, int C, int T, bool raw, bool act) {
+    Cl32 t; t.C = C; t.T = T;
+    const size_t n = (size_t)x.B * (T + 2 * CL_GUARD) * C;
+    if (raw) t.raw = x.c->arena.f(n);
+    if (act) { t.hi = x.c->arena.f(n); t.lo = x.c->arena.f(n); }
+    if (!x.c->arena.dry && act) {                            // only operands are read through the guards (zero padding, conv.py:185-201)
+        launch_cl32_zero_guards(t.hi, x.B, T, C, x.s);
+        launch_cl32_zero_guards(t.lo, x.B, T, C, x.s);
+    }
+    return t;
+}
+static int tc32_conv(Ctx& x, const std::string& key, int kind, int stride, const Cl32& in, const float* residual, bool want_raw, bool want_act,
+                     Cl32* out) {
+    const Tc32W* W;
+    SSRB_TRY(get_tc32w(x.c, key, kind, stride, &W));
+    const int G = CL_GUARD, C = in.C, T = in.T;
+    ConvTc32Args a;
+    a.x_hi = in.hi; a.x_lo = in.lo; a.B = x.B; a.x_bstride = (long long)(T + 2 * G) * C; a.w_hi = W->wh; a.w_lo = W->wl;
+    a.taps = W->taps; a.N = W->N; a.Cw = W->Cw; a.bias = W->bias;
+    int Tout;
+    if (kind == TC_CONV) {
+        SSRB_CHECK(W->Cw == C, ("tc32 conv input width mismatch at " + key).c_str());
+        const int total = W->taps - 1, padL = total - total / 2;
+        Tout = T;
+        a.x_base_off = (long long)(G - padL) * C; a.rows_v = T + G + padL; a.T_rows = T;
+    } else {
+        SSRB_CHECK(W->Cw == stride * C && T % stride == 0, ("tc32 strided conv shape mismatch at " + key).c_str());
+        const int padL = stride - stride / 2;
+        Tout = T / stride;
+        a.x_base_off = (long long)(G - padL) * C;
+        a.rows_v = (int)((a.x_bstride - a.x_base_off) / W->Cw); a.T_rows = Tout;
+    }
+    *out = cl32_alloc(x, W->N, Tout, want_raw, want_act);
+    a.out_raw = out->raw; a.out_hi = out->hi; a.out_lo = out->lo;
+    a.out_bstride = (long long)(Tout + 2 * G) * W->N; a.out_off = (long long)G * W->N;
+    if (residual) { a.res = residual; a.res_bstride = a.out_bstride; a.res_off = a.out_off; }
+    if (x.c->arena.dry) return 0;
+    return conv_tc32(a, x.s);
+}
+// SEANetResnetBlock: y = x + conv_k1(ELU(conv_k3(ELU(x)))); the next layer consumes ELU(y) only
+static int tc32_resblock(Ctx& x, const std::string& prefix, const Cl32& in, Cl32* out) {
+    Cl32 h;
+    SSRB_TRY(tc32_conv(x, prefix + "block.1.conv.conv.", TC_CONV, 1, in, nullptr, false, true, &h));
+    return tc32_conv(x, prefix + "block.3.conv.conv.", TC_CONV, 1, h, in.raw, false, true, out);
+}
+static bool encoder_tc32_supported(ssrb_codec* c, int T) {
+    if (!c->use_tc || c->cfg.n_filters % 64 != 0 || c->cfg.n_filters > 64 || c->cfg.residual_kernel_size != 3 || c->cfg.compress != 2) return false;
+    if (T % c->hop != 0) return false;
+    static const bool off = [] { const char* e = getenv("SSRB_ENC_FP32"); return e && e[0] == '1'; }();   // SSRB_ENC_FP32=1: keep the CUDA-core kernels
+    return !off;
+}
+// SEANetEncoder (seanet.py:63-153) -> latents [B, dimension, T / hop] fp32 channels-first
+static int encoder_tc32(Ctx& x, const std::string& p, const float* wav, int T, Tensor* out) {
+    const int* r = x.c->cfg.ratios;
+    const int er[4] = {r[3], r[2], r[1], r[0]};
+    const ConvW* W0;
+    SSRB_TRY(get_conv(x.c, p + "model.0.conv.conv.", &W0));
+    Cl32 z0 = cl32_alloc(x, W0->d0, T, true, true), cur;
+    if (!x.c->arena.dry) SSRB_TRY(launch_cl32_first_conv(wav, x.B, T, W0->w, W0->b, W0->d0, W0->k, z0.raw, z0.hi, z0.lo, x.s));
+    SSRB_TRY(tc32_resblock(x, p + "model.1.", z0, &cur));
+    for (int st = 1; st <= 3; st++) {
+        Cl32 d, y;
+        const int ci = 3 * st;
+        SSRB_TRY(tc32_conv(x, p + "model." + std::to_string(ci) + ".conv.conv.", TC_CONVS, er[st - 1], cur, nullptr, true, true, &d));
+        SSRB_TRY(tc32_resblock(x, p + "model." + std::to_string(ci + 1) + ".", d, &y));
+        cur = y;
+    }
+    Cl32 d8;
+    SSRB_TRY(tc32_conv(x, p + "model.12.conv.conv.", TC_CONVS, er[3], cur, nullptr, true, false, &d8));
+    Tensor a{x.c->arena.f((size_t)x.B * d8.C * d8.T), d8.C, d8.T}, b;
+    if (!x.c->arena.dry) SSRB_TRY(launch_cl32_to_cf32(d8.raw, x.B, d8.C, d8.T, a.p, x.s));
+    if (x.c->cfg.lstm_layers > 0) { SSRB_TRY(lstm(x, p + "model.13.", a, &b)); } else b = a;
+    return conv(x, p + "model.15.conv.conv.", b, 1, true, nullptr, out);
+}
+
 // runs `fn` twice: a dry pass to size the arena, then for real
 template <typename F>
 static int run_planned(ssrb_codec* c, F fn) {
@@ -604,7 +751,8 @@ int ssrb_codec_encode(ssrb_codec* c, const float* wav, int B, int T, int64_t* co
         SSRB_TRY(run_planned(c, [&]() -> int {
             Ctx x{c, s, nb};
             Tensor in{const_cast<float*>(wav) + (size_t)b0 * T, 1, T}, emb;
-            SSRB_TRY(encoder(x, "encoder.", in, &emb));
+            if (encoder_tc32_supported(c, T)) { SSRB_TRY(encoder_tc32(x, "encoder.", in.p, T, &emb)); }
+            else SSRB_TRY(encoder(x, "encoder.", in, &emb));
             float* ws = c->arena.f((size_t)nb * Tf * Dm);
             if (c->arena.dry) return 0;
             SSRB_CHECK(emb.C == Dm && emb.T == Tf, "encoder output shape mismatch");
