@@ -32,6 +32,7 @@ struct Cl32 { float* raw = nullptr; float* hi = nullptr; float* lo = nullptr; in
 struct LstmW {
     float *wih[4] = {}, *whh[4] = {}, *bsum[4] = {};
     bf16* wih_bf16[4] = {};            // tensor-core input projection (decoder-side LSTMs only)
+    float *wih_hi[4] = {}, *wih_lo[4] = {};   // 3 x TF32 input projection (encoder)
     std::vector<float> bih[4], bhh[4];
     bool has_wih[4] = {}, has_whh[4] = {}, has_b[4] = {};
     int C = 0;
@@ -62,7 +63,22 @@ struct ssrb_codec {
     std::map<std::string, Tc32W> tc32w;
     std::vector<float> wm_embed_host;   // renormalised rows
     bool use_tc = false;
+    bool derived_stale = false;         // a tensor was (re)loaded: repacked copies below are dropped before the next compute call
 };
+
+// the repacked / re-typed weight copies built lazily by the compute paths (tap-major bf16, TF32 hi/lo pairs, bf16 W_ih)
+static void drop_derived(ssrb_codec* c) {
+    cudaDeviceSynchronize();
+    for (auto& kv : c->tcw) { cudaFree(kv.second.w); cudaFree(kv.second.bias); cudaFree(kv.second.bias_alt); }
+    for (auto& kv : c->tc32w) { cudaFree(kv.second.wh); cudaFree(kv.second.wl); cudaFree(kv.second.bias); }
+    c->tcw.clear(); c->tc32w.clear();
+    for (auto& kv : c->lstms)
+        for (int l = 0; l < 4; l++) {
+            cudaFree(kv.second.wih_bf16[l]); cudaFree(kv.second.wih_hi[l]); cudaFree(kv.second.wih_lo[l]);
+            kv.second.wih_bf16[l] = nullptr; kv.second.wih_hi[l] = kv.second.wih_lo[l] = nullptr;
+        }
+    c->derived_stale = false;
+}
 
 static int dalloc(void** p, size_t bytes) { SSRB_CUDA(cudaMalloc(p, bytes ? bytes : 16)); return 0; }
 
@@ -94,9 +110,8 @@ void ssrb_codec_destroy(ssrb_codec* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     for (auto& kv : c->convs) { cudaFree(kv.second.w); cudaFree(kv.second.b); cudaFree(kv.second.wt); }
+    drop_derived(c);
     for (auto& kv : c->lstms) for (int l = 0; l < 4; l++) { cudaFree(kv.second.wih[l]); cudaFree(kv.second.whh[l]); cudaFree(kv.second.bsum[l]); }
-    for (auto& kv : c->tcw) { cudaFree(kv.second.w); cudaFree(kv.second.bias); cudaFree(kv.second.bias_alt); }
-    for (auto& kv : c->tc32w) { cudaFree(kv.second.wh); cudaFree(kv.second.wl); cudaFree(kv.second.bias); }
     cudaFree(c->codebooks); cudaFree(c->cb_sq); cudaFree(c->wm_embed); cudaFree(c->bar); cudaFree(c->arena.base);
     delete c;
 }
@@ -120,6 +135,7 @@ int ssrb_codec_load_tensor(ssrb_codec* c, const char* name_c, const float* host,
     const std::string name(name_c);
     int64_t n = 1;
     for (int i = 0; i < ndim; i++) n *= shape[i];
+    c->derived_stale = true;
     // RVQ codebooks: quantizer.vq.layers.{q}._codebook.embed [bins, dim]
     if (name.rfind("quantizer.vq.layers.", 0) == 0) {
         if (!ends_with(name, "._codebook.embed")) return 0;          // inited / cluster_size / embed_avg: training state
@@ -162,7 +178,7 @@ int ssrb_codec_load_tensor(ssrb_codec* c, const char* name_c, const float* host,
         else if (sub.rfind("weight_hh", 0) == 0) { L.C = (int)shape[1]; SSRB_TRY(upload_new(&L.whh[l], host, n)); L.has_whh[l] = true; }
         else if (sub.rfind("bias_ih", 0) == 0) L.bih[l].assign(host, host + n);
         else if (sub.rfind("bias_hh", 0) == 0) L.bhh[l].assign(host, host + n);
-        if (!L.bih[l].empty() && !L.bhh[l].empty() && !L.has_b[l]) {
+        if (!L.bih[l].empty() && !L.bhh[l].empty() && L.bih[l].size() == L.bhh[l].size()) {      // (re)built whenever either half changes
             std::vector<float> s(L.bih[l].size());
             for (size_t i = 0; i < s.size(); i++) s[i] = L.bih[l][i] + L.bhh[l][i];
             SSRB_TRY(upload_new(&L.bsum[l], s.data(), s.size()));
@@ -255,13 +271,16 @@ __global__ void f32_to_T_kernel(const float* __restrict__ src, T* __restrict__ d
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = from_f32<T>(src[i]);
 }
 // StreamableLSTM (lstm.py:10-25).  tc: input projections x.W_ih^T as bf16 tcgen05 GEMMs (decoder-side LSTMs of the tensor-core path)
-static int lstm(Ctx& x, const std::string& prefix, Tensor in, Tensor* out, bool tc = false) {
+// tc: bf16 tensor-core input projection + mma.sync recurrence (decoder side).  tc32: the input projection as a 3 x TF32 tcgen05 GEMM
+// (conv_tc32 with one tap: fp32-grade), the recurrence stays the fp32 kernel (encoder: its output decides RVQ indices).
+static int lstm(Ctx& x, const std::string& prefix, Tensor in, Tensor* out, bool tc = false, bool tc32 = false) {
     auto it = x.c->lstms.find(prefix);
     if (it == x.c->lstms.end()) { set_error("codec lstm missing: " + prefix); return 1; }
     LstmW& L = it->second;
     const int C = in.C, T = in.T, B = x.B, nl = x.c->cfg.lstm_layers;
     SSRB_CHECK(L.C == C, "lstm width mismatch");
     tc = tc && (C % 64 == 0);
+    tc32 = tc32 && !tc && (C % 32 == 0);
     Arena& A = x.c->arena;
     float* seq = A.f((size_t)T * B * C);
     float* pre = A.f((size_t)T * B * 4 * C);
@@ -269,6 +288,8 @@ static int lstm(Ctx& x, const std::string& prefix, Tensor in, Tensor* out, bool 
     float* hbuf = A.f((size_t)2 * 32 * C);            // fp32 kernel: [2][B][C] fp32; tensor-core kernel: [2][32][C] bf16
     bf16* seq16 = tc ? (bf16*)A.f(((size_t)T * B * C + 1) / 2) : nullptr;
     bf16* hs16 = tc ? (bf16*)A.f(((size_t)T * B * C + 1) / 2) : nullptr;
+    float* x_hi = tc32 ? A.f((size_t)T * B * C) : nullptr;
+    float* x_lo = tc32 ? A.f((size_t)T * B * C) : nullptr;
     out->C = C; out->T = T; out->p = A.f((size_t)B * C * T);
     if (A.dry) return 0;
     SSRB_TRY(launch_bct_to_tbc(in.p, B, C, T, seq, x.s, seq16));
@@ -286,6 +307,18 @@ static int lstm(Ctx& x, const std::string& prefix, Tensor in, Tensor* out, bool 
             }
             g.A = cur16; g.W = L.wih_bf16[l]; g.ab_dtype = SSRB_DTYPE_BF16;
             SSRB_TRY(gemm_tc(g, nullptr, 0, x.s));
+        } else if (tc32) {
+            if (!L.wih_hi[l]) {
+                SSRB_TRY(dalloc((void**)&L.wih_hi[l], (size_t)4 * C * C * 4));
+                SSRB_TRY(dalloc((void**)&L.wih_lo[l], (size_t)4 * C * C * 4));
+                SSRB_TRY(launch_split_tf32(L.wih[l], L.wih_hi[l], L.wih_lo[l], (long long)4 * C * C, x.s));
+            }
+            SSRB_TRY(launch_split_tf32(cur, x_hi, x_lo, (long long)T * B * C, x.s));
+            ConvTc32Args a;                      // pre[T*B, 4C] = seq[T*B, C] . W_ih^T + (b_ih + b_hh): one "utterance" of T*B rows, one tap
+            a.x_hi = x_hi; a.x_lo = x_lo; a.B = 1; a.x_bstride = (long long)T * B * C; a.x_base_off = 0; a.Cw = C; a.rows_v = T * B;
+            a.w_hi = L.wih_hi[l]; a.w_lo = L.wih_lo[l]; a.taps = 1; a.N = 4 * C; a.T_rows = T * B; a.bias = L.bsum[l];
+            a.out_raw = pre; a.out_bstride = 0; a.out_off = 0; a.elu = false;
+            SSRB_TRY(conv_tc32(a, x.s));
         } else {
             g.A = cur; g.W = L.wih[l]; g.ab_dtype = SSRB_DTYPE_F32;
             SSRB_TRY(gemm_simt(g, x.s));
@@ -696,7 +729,7 @@ static int encoder_tc32(Ctx& x, const std::string& p, const float* wav, int T, T
     SSRB_TRY(tc32_conv(x, p + "model.12.conv.conv.", TC_CONVS, er[3], cur, nullptr, true, false, &d8));
     Tensor a{x.c->arena.f((size_t)x.B * d8.C * d8.T), d8.C, d8.T}, b;
     if (!x.c->arena.dry) SSRB_TRY(launch_cl32_to_cf32(d8.raw, x.B, d8.C, d8.T, a.p, x.s));
-    if (x.c->cfg.lstm_layers > 0) { SSRB_TRY(lstm(x, p + "model.13.", a, &b)); } else b = a;
+    if (x.c->cfg.lstm_layers > 0) { SSRB_TRY(lstm(x, p + "model.13.", a, &b, false, true)); } else b = a;
     return conv(x, p + "model.15.conv.conv.", b, 1, true, nullptr, out);
 }
 
@@ -718,6 +751,7 @@ static int run_planned(ssrb_codec* c, F fn) {
 
 int ssrb_codec_check_loaded(ssrb_codec* c) {
     SSRB_CHECK(c, "null argument");
+    if (c->derived_stale) drop_derived(c);
     if (!c->pending.empty()) { set_error("weight_g/weight_v pair incomplete for " + c->pending.begin()->first); return 1; }
     for (int q = 0; q < c->cfg.n_q; q++) if (!c->has_cb[q]) { set_error("codebook missing: " + std::to_string(q)); return 1; }
     return 0;

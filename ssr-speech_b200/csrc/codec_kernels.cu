@@ -465,11 +465,16 @@ int launch_bct_to_btc(const float* in, int B, int C, int T, float* out, cudaStre
 // =================================================================================================
 // LSTM recurrence, persistent + cooperative.          modules/lstm.py:17 (nn.LSTM(dim, dim, 2)); gates i,f,g,o
 //   Each CTA owns 8 hidden units: its 32 rows of W_hh stay resident in shared memory (fp32) for all T
-//   steps; h_{t-1} is exchanged through L2 with one grid-wide barrier per step.
+//   steps; h_{t-1} is exchanged through L2 with one grid-wide barrier per step.  h_{t-1} is staged 8 batch
+//   entries per pass through two shared-memory buffers (cp.async): pass p+1 arrives while pass p is multiplied.
 // =================================================================================================
 constexpr int LSTM_UPB = 8;     // hidden units per CTA
 constexpr int LSTM_BC = 8;      // batch entries staged per pass
-size_t lstm_smem_bytes(int C) { return ((size_t)4 * LSTM_UPB * C + (size_t)LSTM_BC * C + 4 * LSTM_UPB * 32) * 4; }
+size_t lstm_smem_bytes(int C) { return ((size_t)4 * LSTM_UPB * C + (size_t)2 * LSTM_BC * C + 4 * LSTM_UPB * 32) * 4; }
+
+__device__ __forceinline__ void cp_async16_zfill(float* dst_smem, const float* src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src), "r"(src_bytes) : "memory");
+}
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
@@ -478,8 +483,8 @@ __global__ void __launch_bounds__(256) lstm_layer_kernel(const float* __restrict
                                                          int T, int B, int C, bf16* __restrict__ hseq_bf16) {
     extern __shared__ __align__(16) float smem[];
     float* w_s = smem;                               // [32 rows = gate*8+unit][C]
-    float* h_s = w_s + 4 * LSTM_UPB * C;             // [LSTM_BC][C]
-    float* g_s = h_s + LSTM_BC * C;                  // [32 rows][32 batch]
+    float* h_s0 = w_s + 4 * LSTM_UPB * C;            // [2][LSTM_BC][C]
+    float* g_s = h_s0 + 2 * LSTM_BC * C;             // [32 rows][32 batch]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int u0 = blockIdx.x * LSTM_UPB;
     const unsigned int G = gridDim.x;
@@ -497,17 +502,32 @@ __global__ void __launch_bounds__(256) lstm_layer_kernel(const float* __restrict
         pre_v[0] = pr[0]; pre_v[1] = pr[C]; pre_v[2] = pr[2 * C]; pre_v[3] = pr[3 * C];
     }
     __syncthreads();
+    const int npass = (B + LSTM_BC - 1) / LSTM_BC;
+    // one pass of h_{t-1}: LSTM_BC batch entries x C, 16 bytes per request (C % 4 == 0: a request never straddles rows); entries
+    // past the batch are zero-filled (src-size 0).  cp.async.cg reads through L2, where the other CTAs' h_t stores were made
+    // visible by the grid barrier.
+    auto issue_pass = [&](const float* hprev, int b0, float* dst) {
+        const int nb = min(LSTM_BC, B - b0);
+        for (int e = tid * 4; e < LSTM_BC * C; e += 1024) {
+            const int bb = e / C;
+            const bool ok = bb < nb;
+            cp_async16_zfill(dst + e, hprev + (size_t)(b0 + (ok ? bb : 0)) * C + (e - bb * C), ok ? 16 : 0);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
     for (int t = 0; t < T; t++) {
         const float* hprev = hbuf + (size_t)(t & 1) * B * C;
         float* hnext = hbuf + (size_t)((t + 1) & 1) * B * C;
-        for (int b0 = 0; b0 < B; b0 += LSTM_BC) {
+        issue_pass(hprev, 0, h_s0);
+        for (int p = 0; p < npass; p++) {
+            const int b0 = p * LSTM_BC;
             const int nb = min(LSTM_BC, B - b0);
-            __syncthreads();
-            for (int e = tid * 4; e < LSTM_BC * C; e += 1024) {            // C % 4 == 0: a float4 never straddles rows
-                const int bb = e / C;
-                float4 hv = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (bb < nb) hv = __ldcg(reinterpret_cast<const float4*>(hprev + (size_t)(b0 + bb) * C + (e - bb * C)));
-                *reinterpret_cast<float4*>(h_s + e) = hv;
+            const float* h_s = h_s0 + (p & 1) * LSTM_BC * C;
+            if (p + 1 < npass) {
+                issue_pass(hprev, b0 + LSTM_BC, h_s0 + ((p + 1) & 1) * LSTM_BC * C);
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+            } else {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
             }
             __syncthreads();
             // 4 gate rows x 8 batch entries per warp; each lane owns 4 consecutive k per 128-wide slab (LDS.128, no bank
@@ -546,8 +566,8 @@ __global__ void __launch_bounds__(256) lstm_layer_kernel(const float* __restrict
                 const int i = lane / LSTM_BC, j = lane % LSTM_BC;
                 if (j < nb) g_s[(warp * 4 + i) * 32 + ((b0 + j) & 31)] = acc[0];
             }
+            __syncthreads();             // g_s complete; this pass's buffer may be refilled two passes on
         }
-        __syncthreads();
         if (cb < B) {
             const float gi = g_s[(0 * LSTM_UPB + cu) * 32 + cb] + pre_v[0];
             const float gf = g_s[(1 * LSTM_UPB + cu) * 32 + cb] + pre_v[1];

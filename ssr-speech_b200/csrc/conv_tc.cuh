@@ -51,6 +51,7 @@ int launch_cl32_first_conv(const float* wav, int B, int T, const float* W /*[C][
                            float* out_hi, float* out_lo, cudaStream_t s);
 int launch_cl32_zero_guards(float* p, int B, int T, int C, cudaStream_t s);
 int launch_cl32_to_cf32(const float* in, int B, int C, int T, float* out, cudaStream_t s);
+int launch_split_tf32(const float* in, float* hi, float* lo, long long n, cudaStream_t s);   // x = hi + lo, both TF32-representable
 
 // channels-last helpers (codec_cl.cu).  cl tensors: [B][CL_GUARD + T + CL_GUARD][C] bf16.
 int launch_cl_first_conv(const float* wav, int B, int T, const float* W /*[C][1][k]*/, const float* bias, int C, int k,

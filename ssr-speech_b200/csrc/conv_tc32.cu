@@ -315,7 +315,27 @@ __global__ void cl32_to_cf32_kernel(const float* __restrict__ in, int C, int T, 
     }
 }
 
+// x -> (hi, lo) TF32 pair, elementwise (n % 4 == 0)
+__global__ void split_tf32_kernel(const float* __restrict__ in, float* __restrict__ hi, float* __restrict__ lo, long long n4) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = reinterpret_cast<const float4*>(in)[i];
+        float4 h, l;
+        h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
+        l.x = rna_tf32(v.x - h.x); l.y = rna_tf32(v.y - h.y); l.z = rna_tf32(v.z - h.z); l.w = rna_tf32(v.w - h.w);
+        reinterpret_cast<float4*>(hi)[i] = h;
+        reinterpret_cast<float4*>(lo)[i] = l;
+    }
+}
+
 }  // namespace
+
+int launch_split_tf32(const float* in, float* hi, float* lo, long long n, cudaStream_t s) {
+    SSRB_CHECK(n % 4 == 0 && ((uintptr_t)in & 15) == 0 && ((uintptr_t)hi & 15) == 0 && ((uintptr_t)lo & 15) == 0, "split_tf32: 16B alignment");
+    const long long n4 = n / 4;
+    const int grid = (int)std::min<long long>((n4 + 255) / 256, 148 * 8);
+    SSRB_LAUNCH(split_tf32_kernel, grid, 256, 0, s, in, hi, lo, n4);
+    return 0;
+}
 
 int conv_tc32(const ConvTc32Args& a, cudaStream_t s) {
     EncodeTiledFn fn = encode_fn32();

@@ -253,3 +253,38 @@ def test_audio_tokenizer_from_checkpoint_file_matches_direct_model(small, tmp_pa
     assert scale is None and torch.equal(codes, c0) and torch.equal(emb, e0)
     assert torch.equal(tok.decode(codes, None), m.decode(c0))
     assert np.abs(emb.cpu().numpy() - g["ref_emb"]).max() <= 1e-4 * np.abs(g["ref_emb"]).max()
+
+
+def test_reloading_weights_rebuilds_every_derived_copy():
+    """ssrb_codec_load_tensor on a LIVE engine (checkpoint swap through the C ABI, no destroy / create): the lazily repacked
+    copies (tap-major bf16, TF32 hi/lo pairs, bf16 / TF32 W_ih, summed LSTM biases) must follow the new weights, i.e. equal a
+    fresh engine loaded once."""
+    from ssr_speech_b200 import _lib
+    cfg = CodecConfig()
+    sd0, sd1 = make_codec_state_dict(cfg, seed=11), make_codec_state_dict(cfg, seed=12)
+    wav = 0.1 * torch.randn(2, 1, 20 * 320, generator=torch.Generator().manual_seed(3)).cuda()
+    marks = torch.zeros(2, 20, dtype=torch.long, device="cuda")
+    marks[:, 7:13] = 1
+    lib = _lib.load()
+    for precision in ("fp32", "bf16"):
+        swapped = WMEncodecModel(cfg, precision=precision)
+        swapped.load_state_dict(sd0)
+        swapped.to("cuda")
+        c0, _, _ = swapped.encode(wav)
+        swapped.wmdecode(c0, marks, wav)                      # builds the derived copies of sd0
+        h = swapped._engine()
+        fsd = {k: v.detach().cpu().contiguous() for k, v in sd1.items() if torch.is_tensor(v) and v.is_floating_point()}
+        _lib.load_state_dict_into(lib.ssrb_codec_load_tensor, h, fsd)
+        _lib.check(lib.ssrb_codec_check_loaded(h), "ssrb_codec_check_loaded")
+        assert swapped._engine() is h                         # same engine, new weights
+        fresh = WMEncodecModel(cfg, precision=precision)
+        fresh.load_state_dict(sd1)
+        fresh.to("cuda")
+        ca, _, ea = swapped.encode(wav)
+        cb, _, eb = fresh.encode(wav)
+        assert torch.equal(ca, cb) and torch.equal(ea, eb)
+        assert not torch.equal(ca, c0)
+        wa, _ = swapped.wmdecode(ca, marks, wav)
+        wb, _ = fresh.wmdecode(cb, marks, wav)
+        assert torch.equal(wa, wb)
+        assert torch.equal(swapped.decode(ca), fresh.decode(cb))
