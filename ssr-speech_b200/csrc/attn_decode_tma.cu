@@ -298,14 +298,34 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_decode_tma_kernel(const fl
             asm volatile("bar.sync 1, 256;" ::: "memory");
             if (sm_last && d < 128) {
                 __threadfence();
+                // the partials are requested 8 pieces at a time (independent loads: one L2 round trip per 8 pieces, not one per
+                // piece); an absent piece reads as (m, l, o) = (-inf, 0, 0) and adds exact zeros
                 const float* wb = ws + (int64_t)(r * H + h) * max_pieces * 130;
                 float M2 = -INFINITY;
-                for (int j = 0; j < nsp; j++) M2 = fmaxf(M2, __ldcg(wb + j * 130));
+                for (int j0 = 0; j0 < nsp; j0 += 8) {
+                    float mm[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) mm[j] = j0 + j < nsp ? __ldcg(wb + (j0 + j) * 130) : -INFINITY;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) M2 = fmaxf(M2, mm[j]);
+                }
                 float L2 = 0.f, O2 = 0.f;
-                for (int j = 0; j < nsp; j++) {                    // piece order: deterministic
-                    const float wgt = __expf(__ldcg(wb + j * 130) - M2);
-                    L2 += __ldcg(wb + j * 130 + 1) * wgt;
-                    O2 += __ldcg(wb + j * 130 + 2 + d) * wgt;
+                for (int j0 = 0; j0 < nsp; j0 += 8) {              // piece order: deterministic
+                    float mm[8], ll[8], oo[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const bool ok = j0 + j < nsp;
+                        const float* pp = wb + (ok ? j0 + j : j0) * 130;
+                        mm[j] = ok ? __ldcg(pp) : -INFINITY;
+                        ll[j] = ok ? __ldcg(pp + 1) : 0.f;
+                        oo[j] = ok ? __ldcg(pp + 2 + d) : 0.f;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const float wgt = __expf(mm[j] - M2);
+                        L2 += ll[j] * wgt;
+                        O2 += oo[j] * wgt;
+                    }
                 }
                 *op = __float2bfloat16_rn(O2 / L2);
             }

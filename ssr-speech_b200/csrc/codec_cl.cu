@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(256) cl_first_conv_kernel(const float* __restr
         for (int j = 0; j < k; j++) acc = fmaf(ws[c * k + j], xs[tl + j], acc);
         const int64_t o = base + (int64_t)(CL_GUARD + t) * C + c;
         if (out_raw) out_raw[o] = __float2bfloat16_rn(acc);
-        if (out_act) out_act[o] = __float2bfloat16_rn(elu1(acc));
+        if (out_act) out_act[o] = __float2bfloat16_rn(elu1_bf16(acc));
     }
 }
 int launch_cl_first_conv(const float* wav, int B, int T, const float* W, const float* bias, int C, int k, bf16* out_raw,
@@ -94,7 +94,7 @@ __global__ void cf32_to_cl_kernel(const float* __restrict__ in, int C, int T, in
         const int t = t0 + i, c = c0 + threadIdx.x;
         if (t < T && c < C) {
             float v = tile[threadIdx.x][i];
-            if (elu) v = elu1(v);
+            if (elu) v = elu1_bf16(v);
             out[((int64_t)b * (T + 2 * CL_GUARD) + CL_GUARD + t) * C + c] = __float2bfloat16_rn(v);
         }
     }

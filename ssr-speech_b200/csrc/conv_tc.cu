@@ -26,7 +26,11 @@ namespace ssrb {
 
 namespace {
 
-constexpr int BK = 64, ROWS = 128, A_BYTES = ROWS * BK * 2, STAGES = 3;
+constexpr int BK = 64, ROWS = 128, A_BYTES = ROWS * BK * 2, STAGES = 2;
+constexpr int EPI_WARPS = 8;                  // two per TMEM lane group, each takes half of the tile's columns
+constexpr int THREADS = (2 + EPI_WARPS) * 32;
+constexpr int epi_rowb(int NT) { return NT + 16; }               // staging row: NT/2 bf16 + 16 B pad (conflict-free 16 B stores per quarter warp)
+constexpr int epi_bytes(int NT) { return EPI_WARPS * 32 * epi_rowb(NT); }   // one 32-row slab per epilogue warp
 
 struct Maps { CUtensorMap a, w; };
 
@@ -62,41 +66,49 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t
     asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
                  ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum) : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-    uint32_t r[16];
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, float (&v)[16]) {      // caller waits (tcgen05.wait::ld) once for a batch
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]),
+                   "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
                  : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
 
 struct KParams {
     int T_rows, N, nkb_per_tap, taps;
+    int tiles_n, tiles_r, tiles_total;                 // tile t -> n-tile t % tiles_n, row-tile (t / tiles_n) % tiles_r, utterance t / (tiles_n * tiles_r)
     const float* bias; const float* bias_alt; int bias_mod;
     const long long* marks; int marks_T, marks_rep;
     const bf16* res; long long res_bstride, res_off;
     bf16* out_raw; bf16* out_act; long long out_bstride, out_off, valid_lo, valid_hi;
 };
 
+// PERSISTENT: two CTAs per SM walk the tile list with stride gridDim.x.  Three roles, each with its own running counters, so the
+// TMA loads of tile i+1 and its MMAs run under the epilogue of tile i:
+//   warp 0 (one lane)  TMA producer  : k-blocks (tap q, channel block cb) of A [128 rows] and W [NT rows] into a 2-stage ring
+//   warp 1 (one lane)  MMA issuer    : accumulates a tile into TMEM buffer (tile & 1) (2 x NT columns), commits tfull[buf]
+//   warps 2-9          epilogue      : TMEM -> registers (a thread owns a row, a warp half of the columns), releases the buffer as soon as the
+//                                      tile is in registers, then bias / residual / ELU, and stores through a per-warp staging
+//                                      slab so that every global store instruction writes whole 128-byte lines (a thread-per-row
+//                                      store touches 32 lines per instruction and made the LSU the bottleneck).
 template <int NT>
-__global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ Maps maps, const KParams prm) {
-    constexpr int W_BYTES = NT * BK * 2, STAGE_BYTES = A_BYTES + W_BYTES, TMEM_COLS = NT;
+__global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const __grid_constant__ Maps maps, const KParams prm) {
+    constexpr int W_BYTES = NT * BK * 2, STAGE_BYTES = A_BYTES + W_BYTES, TMEM_COLS = 2 * NT;
+    constexpr int CW = NT / 2, ROWB = epi_rowb(NT), LPR = CW / 8;      // columns per epilogue warp, staging row bytes, lanes per staging row
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bar_base = base + STAGES * STAGE_BYTES;
+    const uint32_t epi_base = base + STAGES * STAGE_BYTES;
+    const uint32_t bar_base = epi_base + epi_bytes(NT);
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-    const uint32_t accum_bar = bar_base + 8u * (2 * STAGES), tmem_slot = accum_bar + 8u;
+    auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
+    auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * NT, row0 = blockIdx.y * ROWS, b = blockIdx.z;
     const int nk = prm.taps * prm.nkb_per_tap;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        mbar_init(accum_bar, 1);
+        for (int b = 0; b < 2; b++) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -111,88 +123,130 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ Ma
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int i = 0; i < nk; i++) {
-                const int s = i % STAGES;
-                const uint32_t ph = (i / STAGES) & 1;
-                const int q = i / prm.nkb_per_tap, cb = i - q * prm.nkb_per_tap;
-                mbar_wait(empty_bar(s), ph ^ 1);
-                mbar_expect_tx(full_bar(s), STAGE_BYTES);
-                const uint32_t sp = base + s * STAGE_BYTES;
-                tma_load_3d(sp, &maps.a, full_bar(s), cb * BK, row0 + q, b);
-                tma_load_2d(sp + A_BYTES, &maps.w, full_bar(s), cb * BK, q * prm.N + n0);
+            int it = 0;
+            for (int t = blockIdx.x; t < prm.tiles_total; t += gridDim.x) {
+                const int n0 = (t % prm.tiles_n) * NT, tr = t / prm.tiles_n, row0 = (tr % prm.tiles_r) * ROWS, b = tr / prm.tiles_r;
+                for (int i = 0; i < nk; i++, it++) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    const int q = i / prm.nkb_per_tap, cb = i - q * prm.nkb_per_tap;
+                    mbar_wait(empty_bar(s), ph ^ 1);
+                    mbar_expect_tx(full_bar(s), STAGE_BYTES);
+                    const uint32_t sp = base + s * STAGE_BYTES;
+                    tma_load_3d(sp, &maps.a, full_bar(s), cb * BK, row0 + q, b);
+                    tma_load_2d(sp + A_BYTES, &maps.w, full_bar(s), cb * BK, q * prm.N + n0);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
-            for (int i = 0; i < nk; i++) {
-                const int s = i % STAGES;
-                const uint32_t ph = (i / STAGES) & 1;
-                mbar_wait(full_bar(s), ph);
+            int it = 0, tl = 0;
+            for (int t = blockIdx.x; t < prm.tiles_total; t += gridDim.x, tl++) {
+                const int buf = tl & 1;
+                mbar_wait(tempty_bar(buf), (uint32_t)(((tl >> 1) & 1) ^ 1));          // the epilogue has read this buffer's previous tile
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t sp = base + s * STAGE_BYTES;
-                const uint64_t da = make_desc(sp), db = make_desc(sp + A_BYTES);
+                const uint32_t tacc = tmem_base + (uint32_t)(buf * NT);
+                for (int i = 0; i < nk; i++, it++) {
+                    const int s = it % STAGES;
+                    mbar_wait(full_bar(s), (uint32_t)((it / STAGES) & 1));
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t sp = base + s * STAGE_BYTES;
+                    const uint64_t da = make_desc(sp), db = make_desc(sp + A_BYTES);
 #pragma unroll
-                for (int k = 0; k < BK / 16; k++) umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
-                umma_commit(empty_bar(s));
+                    for (int k = 0; k < BK / 16; k++) umma_bf16(tacc, da + 2 * k, db + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                    umma_commit(empty_bar(s));
+                }
+                umma_commit(tfull_bar(buf));
             }
-            umma_commit(accum_bar);
         }
     } else {
-        const int lg = warp & 3;
-        const int row = row0 + lg * 32 + lane;
-        const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16);
-        mbar_wait(accum_bar, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const bool rok = row < prm.T_rows;
-        const float* bias = prm.bias;
-        if (prm.marks && rok) {
-            int mi = row / prm.marks_rep;
-            if (mi >= prm.marks_T) mi = prm.marks_T - 1;
-            if (prm.marks[(long long)b * prm.marks_T + mi] != 0) bias = prm.bias_alt;
-        }
-#pragma unroll 1
-        for (int c0 = 0; c0 < NT; c0 += 16) {
-            float v[16];
-            tmem_ld16(taddr + c0, v);
-            if (!rok) continue;
-            const int n = n0 + c0;
-            const long long f = (long long)row * prm.N + n;                   // flat index inside the GEMM output
-            if (f + 16 <= prm.valid_lo || f >= prm.valid_hi) continue;
-            const int nb = n % prm.bias_mod;                                  // bias_mod is a multiple of 16
-#pragma unroll
-            for (int j = 0; j < 16; j++) v[j] += bias[nb + j];
-            if (prm.res) {
-                const bf16* rp = prm.res + (long long)b * prm.res_bstride + prm.res_off + f;
-                float r8[8];
-                load8(rp, r8);
-#pragma unroll
-                for (int j = 0; j < 8; j++) v[j] += r8[j];
-                load8(rp + 8, r8);
-#pragma unroll
-                for (int j = 0; j < 8; j++) v[8 + j] += r8[j];
+        const int ew = warp - 2, lg = warp & 3, half = ew >> 2;      // warps 2..9: every (lane group, column half) pair once
+        uint8_t* slab = smem_raw + (epi_base - smem_u32(smem_raw)) + ew * 32 * ROWB;      // this warp's staging slab
+        // read-back / store geometry: LPR lanes cover one staging row, a store instruction writes 32 / LPR whole row segments
+        const int rsub = lane / LPR, piece = lane % LPR;
+        int tl = 0;
+        for (int t = blockIdx.x; t < prm.tiles_total; t += gridDim.x, tl++) {
+            const int n0 = (t % prm.tiles_n) * NT, tr = t / prm.tiles_n, row0 = (tr % prm.tiles_r) * ROWS, b = tr / prm.tiles_r;
+            const int buf = tl & 1;
+            const int ncol = n0 + half * CW;
+            const int row = row0 + lg * 32 + lane;
+            const float* bias = prm.bias;
+            if (prm.marks && row < prm.T_rows) {
+                int mi = row / prm.marks_rep;
+                if (mi >= prm.marks_T) mi = prm.marks_T - 1;
+                if (prm.marks[(long long)b * prm.marks_T + mi] != 0) bias = prm.bias_alt;
             }
-            const long long o = (long long)b * prm.out_bstride + prm.out_off + f;
-            if (f >= prm.valid_lo && f + 16 <= prm.valid_hi) {
-                float lo[8], hi[8];
-                if (prm.out_raw) {
+            mbar_wait(tfull_bar(buf), (uint32_t)((tl >> 1) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * NT + half * CW);
+            float v[CW];
 #pragma unroll
-                    for (int j = 0; j < 8; j++) { lo[j] = v[j]; hi[j] = v[8 + j]; }
-                    store8(prm.out_raw + o, lo);
-                    store8(prm.out_raw + o + 8, hi);
-                }
-                if (prm.out_act) {
+            for (int c = 0; c < CW / 16; c++) tmem_ld16_issue(taddr + c * 16, *reinterpret_cast<float(*)[16]>(&v[c * 16]));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty_bar(buf)) : "memory");
+            {
+                int bi = ncol % prm.bias_mod;                                      // bias_mod is a multiple of 16
 #pragma unroll
-                    for (int j = 0; j < 8; j++) { lo[j] = elu1(v[j]); hi[j] = elu1(v[8 + j]); }
-                    store8(prm.out_act + o, lo);
-                    store8(prm.out_act + o + 8, hi);
+                for (int j = 0; j < CW; j += 4) {
+                    const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + bi));
+                    v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
+                    bi += 4;
+                    if (bi >= prm.bias_mod) bi -= prm.bias_mod;
                 }
-            } else {
-                for (int j = 0; j < 16; j++) {
-                    if (f + j < prm.valid_lo || f + j >= prm.valid_hi) continue;
-                    if (prm.out_raw) prm.out_raw[o + j] = __float2bfloat16_rn(v[j]);
-                    if (prm.out_act) prm.out_act[o + j] = __float2bfloat16_rn(elu1(v[j]));
+            }
+            if (prm.res && row < prm.T_rows) {                                     // unfused residual blocks only (SSRB_RESBLOCK_UNFUSED=1)
+                const bf16* rp = prm.res + (long long)b * prm.res_bstride + prm.res_off + (long long)row * prm.N + ncol;
+#pragma unroll
+                for (int j = 0; j < CW; j += 8) {
+                    float r8[8];
+                    load8(rp + j, r8);
+#pragma unroll
+                    for (int e = 0; e < 8; e++) v[j + e] += r8[e];
                 }
+            }
+            const long long f0 = (long long)(row0 + lg * 32 + rsub) * prm.N + ncol + piece * 8;      // flat index of this lane's first 16 B
+            const long long fstep = (long long)(32 / LPR) * prm.N;
+            const bool inside = row0 + ROWS <= prm.T_rows && (long long)row0 * prm.N + n0 >= prm.valid_lo &&
+                                (long long)(row0 + ROWS - 1) * prm.N + n0 + NT <= prm.valid_hi;
+#pragma unroll
+            for (int pass = 0; pass < 2; pass++) {
+                bf16* outp = pass ? prm.out_act : prm.out_raw;
+                if (!outp) continue;
+                outp += (long long)b * prm.out_bstride + prm.out_off;
+                // a thread's row -> its staging row
+#pragma unroll
+                for (int j = 0; j < CW; j += 8) {
+                    float e8[8];
+#pragma unroll
+                    for (int e = 0; e < 8; e++) e8[e] = pass ? elu1_bf16(v[j + e]) : v[j + e];
+                    store8(reinterpret_cast<bf16*>(slab + lane * ROWB) + j, e8);
+                }
+                __syncwarp();
+                if (inside) {
+#pragma unroll
+                    for (int j = 0; j < LPR; j++)
+                        *reinterpret_cast<uint4*>(outp + f0 + j * fstep) =
+                            *reinterpret_cast<const uint4*>(slab + (j * (32 / LPR) + rsub) * ROWB + piece * 16);
+                } else {
+#pragma unroll 1
+                    for (int j = 0; j < LPR; j++) {
+                        const int grow = row0 + lg * 32 + j * (32 / LPR) + rsub;
+                        const long long f = f0 + j * fstep;
+                        if (grow >= prm.T_rows || f + 8 <= prm.valid_lo || f >= prm.valid_hi) continue;
+                        const uint4 w = *reinterpret_cast<const uint4*>(slab + (j * (32 / LPR) + rsub) * ROWB + piece * 16);
+                        if (f >= prm.valid_lo && f + 8 <= prm.valid_hi) {
+                            *reinterpret_cast<uint4*>(outp + f) = w;
+                        } else {
+                            const bf16* we = reinterpret_cast<const bf16*>(&w);
+                            for (int e = 0; e < 8; e++)
+                                if (f + e >= prm.valid_lo && f + e < prm.valid_hi) outp[f + e] = we[e];
+                        }
+                    }
+                }
+                __syncwarp();
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -221,13 +275,13 @@ EncodeTiledFn encode_fn() {
 
 template <int NT>
 int launch(const Maps& maps, const KParams& prm, dim3 grid, cudaStream_t s) {
-    constexpr size_t SMEM = (size_t)STAGES * (A_BYTES + NT * BK * 2) + 1024 + 256;
+    constexpr size_t SMEM = (size_t)STAGES * (A_BYTES + NT * BK * 2) + epi_bytes(NT) + 1024 + 256;
     static bool done = false;
     if (!done) {
         SSRB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
         done = true;
     }
-    SSRB_LAUNCH(conv_tc_kernel<NT>, grid, 192, SMEM, s, maps, prm);
+    SSRB_LAUNCH(conv_tc_kernel<NT>, grid, THREADS, SMEM, s, maps, prm);
     return 0;
 }
 
@@ -267,8 +321,17 @@ int conv_tc(const ConvTcArgs& a, cudaStream_t s) {
     p.res = a.res; p.res_bstride = a.res_bstride; p.res_off = a.res_off;
     p.out_raw = a.out_raw; p.out_act = a.out_act; p.out_bstride = a.out_bstride; p.out_off = a.out_off;
     p.valid_lo = a.valid_lo; p.valid_hi = a.valid_hi;
-    dim3 grid(a.N / NT, cdiv(a.T_rows, ROWS), a.B);
-    SSRB_CHECK(grid.z <= 65535 && grid.y <= 65535, "conv_tc: grid too large");
+    p.tiles_n = a.N / NT; p.tiles_r = cdiv(a.T_rows, ROWS);
+    const long long total = (long long)p.tiles_n * p.tiles_r * a.B;
+    SSRB_CHECK(total > 0 && total < (1ll << 31), "conv_tc: tile count out of range");
+    p.tiles_total = (int)total;
+    static int n_sm = 0;
+    if (n_sm == 0) {
+        int dev = 0;
+        SSRB_CUDA(cudaGetDevice(&dev));
+        SSRB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    }
+    dim3 grid((unsigned)std::min<long long>(total, 2ll * n_sm));
     return NT == 128 ? launch<128>(maps, p, grid, s) : launch<64>(maps, p, grid, s);
 }
 

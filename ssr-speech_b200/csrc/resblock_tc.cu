@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(192) resblock_tc_kernel(const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 // channels past C/2 (padding of the 32-channel hidden layer) carry zero weights and a zero bias: ELU(0) = 0
-                const float a0 = elu1(v[2 * j] + prm.b1[c0 + 2 * j]), a1 = elu1(v[2 * j + 1] + prm.b1[c0 + 2 * j + 1]);
+                const float a0 = elu1_bf16(v[2 * j] + prm.b1[c0 + 2 * j]), a1 = elu1_bf16(v[2 * j + 1] + prm.b1[c0 + 2 * j + 1]);
                 __nv_bfloat162 h2 = __floats2bfloat162_rn(rok ? a0 : 0.f, rok ? a1 : 0.f);
                 pk[j] = *reinterpret_cast<uint32_t*>(&h2);
             }
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(192) resblock_tc_kernel(const __grid_constant_
             }
             if (prm.out_act) {
 #pragma unroll
-                for (int j = 0; j < 8; j++) { lo[j] = elu1(v[j]); hi[j] = elu1(v[8 + j]); }
+                for (int j = 0; j < 8; j++) { lo[j] = elu1_bf16(v[j]); hi[j] = elu1_bf16(v[8 + j]); }
                 store8(prm.out_act + o, lo);
                 store8(prm.out_act + o + 8, hi);
             }
