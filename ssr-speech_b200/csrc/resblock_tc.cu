@@ -24,7 +24,7 @@ constexpr int BK = 64, ROWS = 128, A_BYTES = ROWS * BK * 2;
 
 struct RbMaps { CUtensorMap a, w1, w2; };
 struct RbParams {
-    int T;
+    int T, tiles_r, tiles_total;                            // tile t -> row tile t % tiles_r of utterance t / tiles_r
     const float* b1; const float* b2;
     const bf16* x_raw; long long x_bstride, x_off;          // skip: x_raw[b * x_bstride + x_off + row * C + c]
     bf16* out_raw; bf16* out_act; long long out_bstride, out_off;
@@ -65,16 +65,15 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t
     asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
                  ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum) : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-    uint32_t r[16];
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, float (&v)[16]) {      // caller waits (tcgen05.wait::ld) once per batch
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]),
+                   "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
                  : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
+
+constexpr int EPI_WARPS = 8;                  // two per TMEM lane group, each takes half of the columns
+constexpr int THREADS = (2 + EPI_WARPS) * 32;
 
 template <int C> struct RbCfg {
     static constexpr int CH = C / 2;
@@ -84,28 +83,40 @@ template <int C> struct RbCfg {
     static constexpr int N2H = C > 256 ? 256 : C;            // UMMA N of GEMM 2 (two instructions side by side when C = 512)
     static constexpr int STAGE1 = A_BYTES + N1 * BK * 2, STAGE2 = C * BK * 2;
     static constexpr int STAGE = STAGE1 > STAGE2 ? STAGE1 : STAGE2;
-    static constexpr int STAGES = C >= 512 ? 2 : 3;
+    static constexpr int STAGES = C == 64 ? 3 : (C == 256 ? 4 : 2);
     static constexpr int H_BYTES = ROWS * N1 * 2;
-    static constexpr int TMEM_COLS = C < 64 ? 64 : C;        // max(N1, C), a power of two >= 32
-    static constexpr size_t SMEM = (size_t)STAGES * STAGE + H_BYTES + 1024 + 256;
+    // tensor memory: acc2 [128 x C] at column 0; acc1 [128 x N1] next to it when both fit in 512 columns, so that GEMM 1 of the
+    // next tile runs under epilogue 2 of this one; C = 512 has to alias them (GEMM 1 then waits for epilogue 2's reads)
+    static constexpr bool ALIAS = C + N1 > 512;
+    static constexpr int ACC1_OFF = ALIAS ? 0 : C;
+    static constexpr int TMEM_NEED = ALIAS ? (C > N1 ? C : N1) : C + N1;
+    static constexpr int TMEM_COLS = TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512);
+    static constexpr int CTAS_PER_SM = C <= 128 ? 2 : 1;
+    // epilogue 2: a warp owns 32 rows x C/2 columns, in chunks of CHUNK columns through a staging slab (row = CHUNK bf16 + 16 B pad)
+    static constexpr int CW2 = C / 2, CHUNK = (C == 64 || C == 512) ? 32 : 64, NCH = CW2 / CHUNK, LPR = CHUNK / 8;
+    static constexpr int SLAB_ROWB = CHUNK * 2 + 16, SLAB_BYTES = 32 * SLAB_ROWB;
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE + H_BYTES + EPI_WARPS * SLAB_BYTES + 1024 + 256;
 };
 
+// PERSISTENT: CTAs walk the tile list (tile = 128 time steps of one utterance) with stride gridDim.x; the TMA producer, the MMA
+// issuer and the 8 epilogue warps each keep running counters, so the loads and GEMM 1 of tile i+1 run under epilogue 2 of tile i.
 template <int C>
-__global__ void __launch_bounds__(192) resblock_tc_kernel(const __grid_constant__ RbMaps maps, const RbParams prm) {
+__global__ void __launch_bounds__(THREADS, RbCfg<C>::CTAS_PER_SM) resblock_tc_kernel(const __grid_constant__ RbMaps maps, const RbParams prm) {
     using Cfg = RbCfg<C>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t hbase = base + Cfg::STAGES * Cfg::STAGE;                      // 1024-aligned: STAGE is a multiple of 1024
-    const uint32_t bar_base = hbase + Cfg::H_BYTES;
+    const uint32_t slab_base = hbase + Cfg::H_BYTES;
+    const uint32_t bar_base = slab_base + EPI_WARPS * Cfg::SLAB_BYTES;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
-    const uint32_t acc1_bar = bar_base + 8u * (2 * Cfg::STAGES), acc2_bar = acc1_bar + 8u, h_bar = acc2_bar + 8u, tmem_slot = h_bar + 8u;
+    const uint32_t acc1_full = bar_base + 8u * (2 * Cfg::STAGES), h_ready = acc1_full + 8u, acc2_full = h_ready + 8u,
+                   acc2_empty = acc2_full + 8u, tmem_slot = acc2_empty + 8u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row0 = blockIdx.x * ROWS, b = blockIdx.y;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < Cfg::STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        mbar_init(acc1_bar, 1); mbar_init(acc2_bar, 1); mbar_init(h_bar, 128);
+        mbar_init(acc1_full, 1); mbar_init(acc2_full, 1); mbar_init(h_ready, EPI_WARPS); mbar_init(acc2_empty, EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -120,22 +131,25 @@ __global__ void __launch_bounds__(192) resblock_tc_kernel(const __grid_constant_
 
     if (warp == 0) {
         if (lane == 0) {
-            // ===== TMA producer: GEMM 1 stages (activation tile of tap q + W1 tile), then GEMM 2 stages (W2 k-blocks), one ring =====
-            for (int i = 0; i < Cfg::NK1 + Cfg::KB2; i++) {
-                const int s = i % Cfg::STAGES;
-                const uint32_t ph = (i / Cfg::STAGES) & 1;
-                mbar_wait(empty_bar(s), ph ^ 1);
-                const uint32_t sp = base + s * Cfg::STAGE;
-                if (i < Cfg::NK1) {
-                    const int q = i / Cfg::KB1, cb = i - q * Cfg::KB1;
-                    mbar_expect_tx(full_bar(s), Cfg::STAGE1);
-                    tma_load_3d(sp, &maps.a, full_bar(s), cb * BK, row0 + q, b);
-                    tma_load_2d(sp + A_BYTES, &maps.w1, full_bar(s), cb * BK, q * Cfg::N1);
-                } else {
-                    const int j = i - Cfg::NK1;
-                    mbar_expect_tx(full_bar(s), Cfg::STAGE2);
-                    tma_load_2d(sp, &maps.w2, full_bar(s), j * BK, 0);
-                    if (C > 256) tma_load_2d(sp + 256 * BK * 2, &maps.w2, full_bar(s), j * BK, 256);
+            // ===== TMA producer: per tile the GEMM 1 stages (activation tile of tap q + W1 tile), then the GEMM 2 stages (W2 k-blocks) =====
+            int it = 0;
+            for (int t = blockIdx.x; t < prm.tiles_total; t += gridDim.x) {
+                const int row0 = (t % prm.tiles_r) * ROWS, b = t / prm.tiles_r;
+                for (int i = 0; i < Cfg::NK1 + Cfg::KB2; i++, it++) {
+                    const int s = it % Cfg::STAGES;
+                    mbar_wait(empty_bar(s), (uint32_t)(((it / Cfg::STAGES) & 1) ^ 1));
+                    const uint32_t sp = base + s * Cfg::STAGE;
+                    if (i < Cfg::NK1) {
+                        const int q = i / Cfg::KB1, cb = i - q * Cfg::KB1;
+                        mbar_expect_tx(full_bar(s), Cfg::STAGE1);
+                        tma_load_3d(sp, &maps.a, full_bar(s), cb * BK, row0 + q, b);
+                        tma_load_2d(sp + A_BYTES, &maps.w1, full_bar(s), cb * BK, q * Cfg::N1);
+                    } else {
+                        const int j = i - Cfg::NK1;
+                        mbar_expect_tx(full_bar(s), Cfg::STAGE2);
+                        tma_load_2d(sp, &maps.w2, full_bar(s), j * BK, 0);
+                        if (C > 256) tma_load_2d(sp + 256 * BK * 2, &maps.w2, full_bar(s), j * BK, 256);
+                    }
                 }
             }
         }
@@ -144,95 +158,145 @@ __global__ void __launch_bounds__(192) resblock_tc_kernel(const __grid_constant_
             // ===== MMA issuer =====
             const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Cfg::N1 >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
             const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Cfg::N2H >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
-            for (int i = 0; i < Cfg::NK1; i++) {
-                const int s = i % Cfg::STAGES;
-                mbar_wait(full_bar(s), (i / Cfg::STAGES) & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t sp = base + s * Cfg::STAGE;
-                const uint64_t da = make_desc(sp), db = make_desc(sp + A_BYTES);
-#pragma unroll
-                for (int k = 0; k < BK / 16; k++) umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc1, (i > 0 || k > 0) ? 1u : 0u);
-                umma_commit(empty_bar(s));
-            }
-            umma_commit(acc1_bar);
-            mbar_wait(h_bar, 0);                                 // h is in shared memory (and acc1 has been read out)
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            for (int j = 0; j < Cfg::KB2; j++) {
-                const int i = Cfg::NK1 + j, s = i % Cfg::STAGES;
-                mbar_wait(full_bar(s), (i / Cfg::STAGES) & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t sp = base + s * Cfg::STAGE;
-                const uint64_t da = make_desc(hbase + j * A_BYTES), db = make_desc(sp);
-#pragma unroll
-                for (int k = 0; k < BK / 16; k++) {
-                    umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc2, (j > 0 || k > 0) ? 1u : 0u);
-                    if (C > 256) umma_bf16(tmem_base + 256, da + 2 * k, make_desc(sp + 256 * BK * 2) + 2 * k, idesc2, (j > 0 || k > 0) ? 1u : 0u);
+            const uint32_t acc1 = tmem_base + Cfg::ACC1_OFF, acc2 = tmem_base;
+            int it = 0, tl = 0;
+            for (int t = blockIdx.x; t < prm.tiles_total; t += gridDim.x, tl++) {
+                const uint32_t tph = (uint32_t)(tl & 1);
+                if (Cfg::ALIAS) {                                   // acc1 shares columns with acc2: the previous tile's epilogue 2 must have read them
+                    mbar_wait(acc2_empty, tph ^ 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 }
-                umma_commit(empty_bar(s));
+                for (int i = 0; i < Cfg::NK1; i++, it++) {
+                    const int s = it % Cfg::STAGES;
+                    mbar_wait(full_bar(s), (uint32_t)((it / Cfg::STAGES) & 1));
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t sp = base + s * Cfg::STAGE;
+                    const uint64_t da = make_desc(sp), db = make_desc(sp + A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; k++) umma_bf16(acc1, da + 2 * k, db + 2 * k, idesc1, (i > 0 || k > 0) ? 1u : 0u);
+                    umma_commit(empty_bar(s));
+                }
+                umma_commit(acc1_full);
+                mbar_wait(h_ready, tph);                            // h is in shared memory (and acc1 has been read out)
+                if (!Cfg::ALIAS) mbar_wait(acc2_empty, tph ^ 1);    // the previous tile's epilogue 2 has read acc2
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int j = 0; j < Cfg::KB2; j++, it++) {
+                    const int s = it % Cfg::STAGES;
+                    mbar_wait(full_bar(s), (uint32_t)((it / Cfg::STAGES) & 1));
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t sp = base + s * Cfg::STAGE;
+                    const uint64_t da = make_desc(hbase + j * A_BYTES), db = make_desc(sp);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; k++) {
+                        umma_bf16(acc2, da + 2 * k, db + 2 * k, idesc2, (j > 0 || k > 0) ? 1u : 0u);
+                        if (C > 256) umma_bf16(acc2 + 256, da + 2 * k, make_desc(sp + 256 * BK * 2) + 2 * k, idesc2, (j > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(empty_bar(s));
+                }
+                umma_commit(acc2_full);
             }
-            umma_commit(acc2_bar);
         }
     } else {
-        // ===== epilogue warps: thread = one time step (row) =====
-        const int lg = warp & 3, rl = lg * 32 + lane;
-        const int row = row0 + rl;
-        const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16);
-        const bool rok = row < prm.T;
-        // ---- epilogue 1: h = ELU(acc1 + b1) -> bf16 -> shared memory in the K-major SWIZZLE_128B layout (16-byte chunk c of row r
-        // sits at chunk c ^ (r & 7) of the row's 128 bytes), k-block jb at hbase + jb * 16 KB ----
-        mbar_wait(acc1_bar, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // ===== epilogue warps: thread = one time step (row); warps 2..9 cover every (lane group, column half) pair once =====
+        const int ew = warp - 2, lg = warp & 3, half = ew >> 2, rl = lg * 32 + lane;
+        uint8_t* slab = smem_raw + (slab_base - smem_u32(smem_raw)) + ew * Cfg::SLAB_BYTES;
+        const int rsub = lane / Cfg::LPR, piece = lane % Cfg::LPR;            // staged copies: LPR lanes cover one staging row
+        constexpr int RSTEP = 32 / Cfg::LPR;
+        int tl = 0;
+        for (int t = blockIdx.x; t < prm.tiles_total; t += gridDim.x, tl++) {
+            const int row0 = (t % prm.tiles_r) * ROWS, b = t / prm.tiles_r;
+            const uint32_t tph = (uint32_t)(tl & 1);
+            const int row = row0 + rl;
+            const bool rok = row < prm.T;
+            const uint32_t tlane = tmem_base + ((uint32_t)(lg * 32) << 16);
+            // ---- epilogue 1: h = ELU(acc1 + b1) -> bf16 -> shared memory in the K-major SWIZZLE_128B layout (16-byte chunk c of row r
+            // sits at chunk c ^ (r & 7) of the row's 128 bytes), k-block jb at hbase + jb * 16 KB; this warp's half of the N1 columns ----
+            mbar_wait(acc1_full, tph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-        for (int c0 = 0; c0 < Cfg::N1; c0 += 16) {
-            float v[16];
-            tmem_ld16(taddr + c0, v);
-            uint32_t pk[8];
+            for (int c0 = half * (Cfg::N1 / 2); c0 < (half + 1) * (Cfg::N1 / 2); c0 += 16) {
+                float v[16];
+                tmem_ld16_issue(tlane + Cfg::ACC1_OFF + c0, v);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                uint32_t pk[8];
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                // channels past C/2 (padding of the 32-channel hidden layer) carry zero weights and a zero bias: ELU(0) = 0
-                const float a0 = elu1_bf16(v[2 * j] + prm.b1[c0 + 2 * j]), a1 = elu1_bf16(v[2 * j + 1] + prm.b1[c0 + 2 * j + 1]);
-                __nv_bfloat162 h2 = __floats2bfloat162_rn(rok ? a0 : 0.f, rok ? a1 : 0.f);
-                pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+                for (int j = 0; j < 4; j++) {
+                    // channels past C/2 (padding of the 32-channel hidden layer) carry zero weights and a zero bias: ELU(0) = 0
+                    const float4 bv = __ldg(reinterpret_cast<const float4*>(prm.b1 + c0 + 4 * j));
+                    const float a0 = elu1_bf16(v[4 * j] + bv.x), a1 = elu1_bf16(v[4 * j + 1] + bv.y);
+                    const float a2 = elu1_bf16(v[4 * j + 2] + bv.z), a3 = elu1_bf16(v[4 * j + 3] + bv.w);
+                    __nv_bfloat162 h01 = __floats2bfloat162_rn(rok ? a0 : 0.f, rok ? a1 : 0.f), h23 = __floats2bfloat162_rn(rok ? a2 : 0.f, rok ? a3 : 0.f);
+                    pk[2 * j] = *reinterpret_cast<uint32_t*>(&h01);
+                    pk[2 * j + 1] = *reinterpret_cast<uint32_t*>(&h23);
+                }
+                const int jb = c0 >> 6, ch = (c0 & 63) >> 3;        // k-block, first of the two 16-byte chunks
+                const uint32_t rowb = hbase + (uint32_t)(jb * A_BYTES + rl * 128);
+                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(rowb + (uint32_t)(((ch) ^ (rl & 7)) * 16)), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(rowb + (uint32_t)(((ch + 1) ^ (rl & 7)) * 16)), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
             }
-            const int jb = c0 >> 6, ch = (c0 & 63) >> 3;        // k-block, first of the two 16-byte chunks
-            const uint32_t rowb = hbase + (uint32_t)(jb * A_BYTES + rl * 128);
-            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(rowb + (uint32_t)(((ch) ^ (rl & 7)) * 16)), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
-            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(rowb + (uint32_t)(((ch + 1) ^ (rl & 7)) * 16)), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
-        }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");           // generic-proxy stores -> visible to the tensor core's reads
-        mbar_arrive(h_bar);
-        // ---- epilogue 2: y = acc2 + b2 + x ----
-        mbar_wait(acc2_bar, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");           // generic-proxy stores -> visible to the tensor core's reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive(h_ready);
+            // ---- epilogue 2: y = acc2 + b2 + x, this warp's C/2 columns in chunks; residual in and both outputs go through the staging
+            // slab so that every global access instruction covers whole row segments ----
+            mbar_wait(acc2_full, tph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const long long xrow0 = (long long)b * prm.x_bstride + prm.x_off + (long long)(row0 + lg * 32) * C;
+            const long long orow0 = (long long)b * prm.out_bstride + prm.out_off + (long long)(row0 + lg * 32) * C;
+            const bool full_rows = row0 + lg * 32 + 32 <= prm.T;
 #pragma unroll 1
-        for (int c0 = 0; c0 < C; c0 += 16) {
-            float v[16];
-            tmem_ld16(taddr + c0, v);
-            if (!rok) continue;
+            for (int ch = 0; ch < Cfg::NCH; ch++) {
+                const int col0 = half * Cfg::CW2 + ch * Cfg::CHUNK;
+                float v[Cfg::CHUNK];
 #pragma unroll
-            for (int j = 0; j < 16; j++) v[j] += prm.b2[c0 + j];
-            const bf16* rp = prm.x_raw + (long long)b * prm.x_bstride + prm.x_off + (long long)row * C + c0;
-            float r8[8];
-            load8(rp, r8);
+                for (int c = 0; c < Cfg::CHUNK / 16; c++) tmem_ld16_issue(tlane + col0 + c * 16, *reinterpret_cast<float(*)[16]>(&v[c * 16]));
+                // the skip rows of this chunk: coalesced global -> slab
 #pragma unroll
-            for (int j = 0; j < 8; j++) v[j] += r8[j];
-            load8(rp + 8, r8);
+                for (int j = 0; j < Cfg::LPR; j++) {
+                    const int rr = j * RSTEP + rsub;
+                    uint4 w = make_uint4(0u, 0u, 0u, 0u);
+                    if (full_rows || row0 + lg * 32 + rr < prm.T) w = *reinterpret_cast<const uint4*>(prm.x_raw + xrow0 + (long long)rr * C + col0 + piece * 8);
+                    *reinterpret_cast<uint4*>(slab + rr * Cfg::SLAB_ROWB + piece * 16) = w;
+                }
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (ch == Cfg::NCH - 1) {                           // acc2 is in registers: the tensor core may overwrite it
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acc2_empty);
+                } else {
+                    __syncwarp();
+                }
 #pragma unroll
-            for (int j = 0; j < 8; j++) v[8 + j] += r8[j];
-            const long long o = (long long)b * prm.out_bstride + prm.out_off + (long long)row * C + c0;
-            float lo[8], hi[8];
-            if (prm.out_raw) {
+                for (int j = 0; j < Cfg::CHUNK; j += 8) {
+                    float r8[8];
+                    load8(reinterpret_cast<const bf16*>(slab + lane * Cfg::SLAB_ROWB) + j, r8);
+                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(prm.b2 + col0 + j)), b1 = __ldg(reinterpret_cast<const float4*>(prm.b2 + col0 + j + 4));
+                    v[j] += r8[0] + b0.x; v[j + 1] += r8[1] + b0.y; v[j + 2] += r8[2] + b0.z; v[j + 3] += r8[3] + b0.w;
+                    v[j + 4] += r8[4] + b1.x; v[j + 5] += r8[5] + b1.y; v[j + 6] += r8[6] + b1.z; v[j + 7] += r8[7] + b1.w;
+                }
+                __syncwarp();
 #pragma unroll
-                for (int j = 0; j < 8; j++) { lo[j] = v[j]; hi[j] = v[8 + j]; }
-                store8(prm.out_raw + o, lo);
-                store8(prm.out_raw + o + 8, hi);
-            }
-            if (prm.out_act) {
+                for (int pass = 0; pass < 2; pass++) {
+                    bf16* outp = pass ? prm.out_act : prm.out_raw;
+                    if (!outp) continue;
 #pragma unroll
-                for (int j = 0; j < 8; j++) { lo[j] = elu1_bf16(v[j]); hi[j] = elu1_bf16(v[8 + j]); }
-                store8(prm.out_act + o, lo);
-                store8(prm.out_act + o + 8, hi);
+                    for (int j = 0; j < Cfg::CHUNK; j += 8) {
+                        float e8[8];
+#pragma unroll
+                        for (int e = 0; e < 8; e++) e8[e] = pass ? elu1_bf16(v[j + e]) : v[j + e];
+                        store8(reinterpret_cast<bf16*>(slab + lane * Cfg::SLAB_ROWB) + j, e8);
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < Cfg::LPR; j++) {
+                        const int rr = j * RSTEP + rsub;
+                        if (full_rows || row0 + lg * 32 + rr < prm.T)
+                            *reinterpret_cast<uint4*>(outp + orow0 + (long long)rr * C + col0 + piece * 8) =
+                                *reinterpret_cast<const uint4*>(slab + rr * Cfg::SLAB_ROWB + piece * 16);
+                    }
+                    __syncwarp();
+                }
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -260,13 +324,15 @@ EncodeTiledFn encode_fn_rb() {
 }
 
 template <int C>
-int launch_rb(const RbMaps& maps, const RbParams& prm, dim3 grid, cudaStream_t s) {
+int launch_rb(const RbMaps& maps, const RbParams& prm, dim3 grid, int n_sm, cudaStream_t s) {
     static bool done = false;
     if (!done) {
         SSRB_CUDA(cudaFuncSetAttribute(resblock_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RbCfg<C>::SMEM));
         done = true;
     }
-    SSRB_LAUNCH(resblock_tc_kernel<C>, grid, 192, RbCfg<C>::SMEM, s, maps, prm);
+    static_assert(RbCfg<C>::SMEM <= 232448, "resblock_tc: shared memory budget");
+    grid.x = std::min<unsigned>(grid.x, RbCfg<C>::CTAS_PER_SM * (unsigned)n_sm);
+    SSRB_LAUNCH(resblock_tc_kernel<C>, grid, THREADS, RbCfg<C>::SMEM, s, maps, prm);
     return 0;
 }
 
@@ -310,13 +376,22 @@ int resblock_tc(const ResblockTcArgs& a, cudaStream_t s) {
     p.T = a.T; p.b1 = a.b1; p.b2 = a.b2;
     p.x_raw = a.x_raw; p.x_bstride = a.x_bstride; p.x_off = a.x_raw_off;
     p.out_raw = a.out_raw; p.out_act = a.out_act; p.out_bstride = a.out_bstride; p.out_off = a.out_off;
-    dim3 grid(cdiv(a.T, ROWS), a.B);
-    SSRB_CHECK(grid.y <= 65535, "resblock_tc: batch too large");
+    p.tiles_r = cdiv(a.T, ROWS);
+    const long long total = (long long)p.tiles_r * a.B;
+    SSRB_CHECK(total > 0 && total < (1ll << 31), "resblock_tc: tile count out of range");
+    p.tiles_total = (int)total;
+    static int n_sm = 0;
+    if (n_sm == 0) {
+        int dev = 0;
+        SSRB_CUDA(cudaGetDevice(&dev));
+        SSRB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    }
+    dim3 grid((unsigned)total);                             // capped to the resident CTA count in launch_rb
     switch (C) {
-        case 64: return launch_rb<64>(maps, p, grid, s);
-        case 128: return launch_rb<128>(maps, p, grid, s);
-        case 256: return launch_rb<256>(maps, p, grid, s);
-        default: return launch_rb<512>(maps, p, grid, s);
+        case 64: return launch_rb<64>(maps, p, grid, n_sm, s);
+        case 128: return launch_rb<128>(maps, p, grid, n_sm, s);
+        case 256: return launch_rb<256>(maps, p, grid, n_sm, s);
+        default: return launch_rb<512>(maps, p, grid, n_sm, s);
     }
 }
 
