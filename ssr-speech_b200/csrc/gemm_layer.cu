@@ -1,6 +1,7 @@
 // gemm_layer.cu — EXPERIMENTAL persistent per-layer GEMM chain for the decode iteration (off by default:
-// SSRB_LAYER_KERNEL=1).  sm_100a only.  NOT yet verified on hardware (written after this round's GPU budget was spent); the
-// per-GEMM chain of gemm_tc.cu stays the product path until tests/test_gpu_layer_kernel.py is green on a B200.
+// SSRB_LAYER_KERNEL=1).  sm_100a only.  Verified and A/B'd on a B200 in round 2 (profiles/r02a_summary.md): correct, but slower
+// than the per-GEMM chain (its grid barriers cost what the kernel boundaries cost: iteration 1.79 -> 1.95 ms); the
+// per-GEMM chain of gemm_tc.cu stays the product path.
 //
 // Why: inside a decode iteration the GEMM phase of a layer is latency-bound — 38 us for a 15.4 us weight stream
 // (profiles/r01e_summary.md): each of the four launches pays activation tile, accumulate, park, cluster barrier, DSMEM
