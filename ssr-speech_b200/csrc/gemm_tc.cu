@@ -435,6 +435,9 @@ __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.w
 // its global stores (the barrier only protects the peers' shared memory; measured +1.3 % decode throughput).
 // =================================================================================================================
 enum { ROLE_QKV = 1, ROLE_RES = 2, ROLE_FFN1 = 3 };
+#ifndef DEC_STAGES_Q16
+#define DEC_STAGES_Q16 6
+#endif
 #ifndef DEC_EARLY_ARRIVE
 #define DEC_EARLY_ARRIVE 1
 #endif
@@ -443,7 +446,9 @@ enum { ROLE_QKV = 1, ROLE_RES = 2, ROLE_FFN1 = 3 };
 #endif
 
 template <int QROWS> struct DecCfg : TcCfg<QROWS> {
-    static constexpr int STAGES = QROWS >= 128 ? 3 : DEC_STAGES;
+    // small batches (16 / 32 activation rows): the activation tile is 2-4 KB, so a deeper ring fits two CTAs per SM — more of the
+    // weight stream is requested before griddepcontrol.wait, which is the only overlap a 4-7 us GEMM has
+    static constexpr int STAGES = QROWS >= 128 ? 3 : (DEC_STAGES == 4 && QROWS <= 16 ? DEC_STAGES_Q16 : (DEC_STAGES == 4 && QROWS <= 32 ? 5 : DEC_STAGES));
     static constexpr int RING_BYTES = STAGES * TcCfg<QROWS>::STAGE_BYTES;
     static_assert(TcCfg<QROWS>::PART_BYTES <= RING_BYTES, "partial tile must fit in the drained TMA ring");
     static constexpr size_t SMEM = (size_t)RING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
