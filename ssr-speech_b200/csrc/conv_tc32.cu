@@ -90,8 +90,10 @@ struct K32Params {
 // run (the promotion trick fp8 GEMMs use).
 constexpr int CHUNK_KB = 4;
 
+constexpr int EPI32_WARPS = 8, THREADS32 = (2 + EPI32_WARPS) * 32;     // two epilogue warps per TMEM lane group, each takes half of the columns
+
 template <int NT, int STAGES>
-__global__ void __launch_bounds__(192) conv_tc32_kernel(const __grid_constant__ Maps32 maps, const K32Params prm) {
+__global__ void __launch_bounds__(THREADS32, (NT == 128 && STAGES == 1) ? 2 : 1) conv_tc32_kernel(const __grid_constant__ Maps32 maps, const K32Params prm) {
     constexpr int W_BYTES = NT * BK * 4, STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES, TMEM_COLS = 2 * NT;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -106,7 +108,7 @@ __global__ void __launch_bounds__(192) conv_tc32_kernel(const __grid_constant__ 
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int i = 0; i < 2; i++) { mbar_init(tfull0 + 8u * i, 1); mbar_init(tempty0 + 8u * i, 4); }
+        for (int i = 0; i < 2; i++) { mbar_init(tfull0 + 8u * i, 1); mbar_init(tempty0 + 8u * i, EPI32_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -165,19 +167,20 @@ __global__ void __launch_bounds__(192) conv_tc32_kernel(const __grid_constant__ 
             }
         }
     } else {
-        const int lg = warp & 3;
+        constexpr int CW = NT / 2;                                   // columns of this warp
+        const int lg = warp & 3, half = (warp - 2) >> 2;             // warps 2..9: every (lane group, column half) pair once
         const int row = row0 + lg * 32 + lane;
         const bool rok = row < prm.T_rows;
-        float acc[NT];
+        float acc[CW];
 #pragma unroll
-        for (int j = 0; j < NT; j++) acc[j] = 0.f;
+        for (int j = 0; j < CW; j++) acc[j] = 0.f;
         for (int c = 0; c < nchunks; c++) {
             const int buf = c & 1;
             mbar_wait(tfull0 + 8u * buf, (uint32_t)((c >> 1) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * NT);
+            const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * NT + half * CW);
 #pragma unroll
-            for (int c0 = 0; c0 < NT; c0 += 16) {
+            for (int c0 = 0; c0 < CW; c0 += 16) {
                 float v[16];
                 tmem_ld16(taddr + c0, v);
 #pragma unroll
@@ -189,8 +192,8 @@ __global__ void __launch_bounds__(192) conv_tc32_kernel(const __grid_constant__ 
         }
         if (rok) {
 #pragma unroll
-            for (int c0 = 0; c0 < NT; c0 += 16) {
-                const int n = n0 + c0;
+            for (int c0 = 0; c0 < CW; c0 += 16) {
+                const int n = n0 + half * CW + c0;
                 const long long f = (long long)row * prm.N + n;
                 float v[16];
 #pragma unroll
@@ -258,7 +261,7 @@ int launch32(const Maps32& maps, const K32Params& prm, dim3 grid, cudaStream_t s
         SSRB_CUDA(cudaFuncSetAttribute(conv_tc32_kernel<NT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
         done = true;
     }
-    SSRB_LAUNCH((conv_tc32_kernel<NT, STAGES>), grid, 192, SMEM, s, maps, prm);
+    SSRB_LAUNCH((conv_tc32_kernel<NT, STAGES>), grid, THREADS32, SMEM, s, maps, prm);
     return 0;
 }
 
@@ -374,7 +377,10 @@ int conv_tc32(const ConvTc32Args& a, cudaStream_t s) {
     SSRB_CHECK(!a.out_hi == !a.out_lo, "conv_tc32: hi and lo outputs go together");
     dim3 grid(a.N / NT, cdiv(a.T_rows, ROWS), a.B);
     SSRB_CHECK(grid.z <= 65535 && grid.y <= 65535, "conv_tc32: grid too large");
-    if (NT == 128) return launch32<128, 3>(maps, p, grid, s);
+#ifndef C32_STAGES_128
+#define C32_STAGES_128 3          // measured on 32 x 10 s: 3 stages 38.1 ms, 2 stages 39.5 ms, 1 stage with two CTAs per SM 38.5 ms
+#endif
+    if (NT == 128) return launch32<128, C32_STAGES_128>(maps, p, grid, s);
     if (NT == 64) return launch32<64, 2>(maps, p, grid, s);
     return launch32<32, 2>(maps, p, grid, s);
 }
