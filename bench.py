@@ -390,6 +390,8 @@ def main():
     wavs = [w.pin_memory() for w in wavs]
     dc = decode_config()
     T = wavs[0].shape[-1]
+    # one pinned result buffer for the whole run, as a serving loop would keep (results are copied into it asynchronously)
+    host_out = torch.empty(args.batch, 1, (T // 320 + 10 * args.lx) * 320, dtype=torch.float32).pin_memory()
     gen_frames = 10 * args.lx - (T // 320 + 10) + 1
     tokens_per_step = args.batch * K_CODEBOOKS * gen_frames            # per rank
 
@@ -397,7 +399,7 @@ def main():
         # N > 1: the finished waveforms stay in HBM, ONE NCCL all_gather over NVLink, then ONE device-to-host copy
         out, results = pipeline.inference_batch(model, tok, wavs, texts, spans, dc, cfg_coef=1.5, cfg_stride=5, aug_text=True,
                                                 use_watermark=not args.no_watermark, tts=True, seed=1000, timings=timings,
-                                                to_host=(world == 1))
+                                                to_host=(world == 1), host_out=host_out if world == 1 else None)
         if world > 1:
             out = gather_waveforms(out, device=dev, to_host=True)
         return out, results
@@ -431,8 +433,9 @@ def main():
     barrier()
     e2e_ms = e0.elapsed_time(e1)
     launches = lib.ssrb_launch_count() - launches0
-    h2d = sum(w.numel() * 4 for w in wavs) + sum(t.numel() * 4 for t in texts) * 2 \
-        + args.batch * (T // 320 + gen_frames) * 320 * 4 * (0 if args.no_watermark else 1)
+    # the waveforms cross the bus once (the watermark decoder's new_wav is spliced on the device from the encoder's copy);
+    # text ids as int32 for the cond and the uncond row
+    h2d = sum(w.numel() * 4 for w in wavs) + sum(t.numel() * 4 for t in texts) * 2
     # per rank: its own waveforms at N = 1; at N > 1 every rank reads the whole gathered job back in one copy
     d2h = sum(o.numel() * 4 for o in out) + args.batch * K_CODEBOOKS * (gen_frames + 4) * 4
 

@@ -15,20 +15,31 @@ __global__ void __launch_bounds__(256) cl_first_conv_kernel(const float* __restr
         const int g = t0 + e - padL;
         xs[e] = (g >= 0 && g < T) ? wav[(int64_t)b * T + g] : 0.f;
     }
-    for (int e = threadIdx.x; e < C * k; e += 256) ws[e] = W[e];
+    for (int e = threadIdx.x; e < C * k; e += 256) { const int cc = e / k, j = e - cc * k; ws[j * 64 + cc] = W[e]; }      // [tap][channel]: conflict-free pairs
     __syncthreads();
-    const int c = threadIdx.x % 64, tg = threadIdx.x / 64;
+    // a thread owns two adjacent channels (one 4-byte store per output array and time step; a warp writes one whole 128-byte row when
+    // C = 64) and every 8th time step of the tile
+    const int c = 2 * (threadIdx.x % 32), tg = threadIdx.x / 32;
     if (c >= C) return;
-    const float bv = bias[c];
+    const bool two = c + 1 < C;
+    const float b0 = bias[c], b1 = two ? bias[c + 1] : 0.f;
     const int64_t base = (int64_t)b * (T + 2 * CL_GUARD) * C;
-    for (int i = 0; i < 16; i++) {
-        const int tl = tg + 4 * i, t = t0 + tl;
+    for (int i = 0; i < 8; i++) {
+        const int tl = tg + 8 * i, t = t0 + tl;
         if (t >= T) break;
-        float acc = bv;
-        for (int j = 0; j < k; j++) acc = fmaf(ws[c * k + j], xs[tl + j], acc);
+        float a0 = b0, a1 = b1;
+        for (int j = 0; j < k; j++) {
+            a0 = fmaf(ws[j * 64 + c], xs[tl + j], a0);
+            if (two) a1 = fmaf(ws[j * 64 + c + 1], xs[tl + j], a1);
+        }
         const int64_t o = base + (int64_t)(CL_GUARD + t) * C + c;
-        if (out_raw) out_raw[o] = __float2bfloat16_rn(acc);
-        if (out_act) out_act[o] = __float2bfloat16_rn(elu1_bf16(acc));
+        if (two && (C & 1) == 0) {
+            if (out_raw) *reinterpret_cast<__nv_bfloat162*>(out_raw + o) = __floats2bfloat162_rn(a0, a1);
+            if (out_act) *reinterpret_cast<__nv_bfloat162*>(out_act + o) = __floats2bfloat162_rn(elu1_bf16(a0), elu1_bf16(a1));
+        } else {
+            if (out_raw) { out_raw[o] = __float2bfloat16_rn(a0); if (two) out_raw[o + 1] = __float2bfloat16_rn(a1); }
+            if (out_act) { out_act[o] = __float2bfloat16_rn(elu1_bf16(a0)); if (two) out_act[o + 1] = __float2bfloat16_rn(elu1_bf16(a1)); }
+        }
     }
 }
 int launch_cl_first_conv(const float* wav, int B, int T, const float* W, const float* bias, int C, int k, bf16* out_raw,

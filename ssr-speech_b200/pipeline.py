@@ -74,27 +74,39 @@ def splice_original(wav: torch.Tensor, n_frames: int, masks, ori_masks, hop: int
     return new_wav
 
 
+def splice_original_device(wav_dev: torch.Tensor, out: torch.Tensor, masks, ori_masks, hop: int = 320) -> None:
+    """splice_original on tensors that are already in HBM: wav_dev [1, T] is the utterance's original waveform (the encode input),
+    out [1, n_frames * hop] is zero-initialised; the kept intervals are device-to-device slice copies."""
+    for (na, nb), (oa, ob) in zip(masks, ori_masks):
+        na, oa = max(na, 0), max(oa, 0)
+        if nb > na:
+            out[:, na * hop:nb * hop] = wav_dev[:1, oa * hop:ob * hop]
+
+
 @torch.no_grad()
 def inference_batch(model, audio_tokenizer: AudioTokenizer, wavs: List[torch.Tensor], text_ids: List[torch.Tensor],
                     mask_intervals: List, decode_config: Dict, cfg_coef: float = 1.5, cfg_stride: int = 5,
                     aug_text: bool = True, use_watermark: bool = True, tts: bool = True, seed: Optional[int] = None,
-                    timings: Optional[Dict[str, float]] = None, to_host: bool = True):
+                    timings: Optional[Dict[str, float]] = None, to_host: bool = True,
+                    host_out: Optional[torch.Tensor] = None):
     """Batched hot path with HOST inputs/outputs (this is what bench.py's `e2e` measures).
 
-    wavs[i]: float32 [1, T_i] host tensors at 16 kHz (T_i multiple of 320, equal within the batch);
-    text_ids[i]: int64 [Lx_i]; mask_intervals[i]: [M_i, 2] frames.  Returns a list of host waveforms [1, T_out_i];
-    `to_host=False` leaves them in HBM (multi-GPU jobs gather on the device first and copy to the host once,
-    dist.gather_waveforms)."""
+    wavs[i]: float32 [1, T_i] host tensors at 16 kHz (T_i multiple of 320, equal within the batch; pinned tensors are copied
+    asynchronously); text_ids[i]: int64 [Lx_i]; mask_intervals[i]: [M_i, 2] frames.  Returns a list of host waveforms [1, T_out_i].
+    The original waveforms cross the bus ONCE: the watermark decoder's `new_wav` (inference_scale.py:66-78) is spliced from the
+    device copy the encoder already used.  `host_out` (optional, pinned, [U, 1, >= longest output]): the results are copied into it
+    asynchronously and the returned tensors are views of it — a serving loop reuses one such buffer instead of paying a pageable
+    allocation + staged copy per batch.  `to_host=False` leaves the results in HBM (multi-GPU jobs gather on the device first
+    and copy to the host once, dist.gather_waveforms)."""
     dev = audio_tokenizer.device
     U = len(wavs)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     T = wavs[0].shape[-1]
     assert all(w.shape[-1] == T for w in wavs), "equal-length prompts per batch (pad on the caller side)"
     ev[0].record()
-    wav_host = torch.stack(wavs, 0)                                                   # [U,1,T]
-    if not wav_host.is_pinned():
-        wav_host = wav_host.pin_memory()
-    wav_dev = wav_host.to(dev, non_blocking=True)
+    wav_dev = torch.empty(U, 1, T, dtype=torch.float32, device=dev)
+    for i, w in enumerate(wavs):
+        wav_dev[i].copy_(w.reshape(1, T).to(torch.float32), non_blocking=True)
     codes, scale, _ = audio_tokenizer.encode(wav_dev)                                 # [U,K,Tf]
     ev[1].record()
     ys = [codes[i].transpose(0, 1) for i in range(U)]                                 # [Tf,K]
@@ -112,14 +124,24 @@ def inference_batch(model, audio_tokenizer: AudioTokenizer, wavs: List[torch.Ten
     for n_frames, idxs in by_len.items():
         fr = torch.cat([results[i][0] for i in idxs], 0).to(dev)
         if use_watermark:
-            mk = torch.cat([results[i][1] for i in idxs], 0).to(dev)
-            nw = torch.stack([splice_original(wavs[i], n_frames, results[i][2], results[i][3]) for i in idxs], 0)
-            gen = audio_tokenizer.wmdecode(fr, mk, nw.to(dev, non_blocking=True), scale)
+            mk = torch.cat([results[i][1] for i in idxs], 0).to(dev, non_blocking=True)
+            nw = torch.zeros(len(idxs), 1, n_frames * 320, dtype=torch.float32, device=dev)
+            for j, i in enumerate(idxs):
+                splice_original_device(wav_dev[i], nw[j], results[i][2], results[i][3])
+            gen = audio_tokenizer.wmdecode(fr, mk, nw, scale)
         else:
             gen = audio_tokenizer.decode(fr, scale)
-        gen_h = gen.to("cpu") if to_host else gen
+        if not to_host:
+            gen_h = gen
+        elif host_out is not None:
+            assert host_out.is_pinned() and host_out.shape[0] >= U and host_out.shape[-1] >= gen.shape[-1], "host_out: pinned [U, 1, >= T_out]"
+            for j, i in enumerate(idxs):
+                host_out[i, :, :gen.shape[-1]].copy_(gen[j], non_blocking=True)       # completes before the synchronize below
+            gen_h = None
+        else:
+            gen_h = gen.to("cpu")
         for j, i in enumerate(idxs):
-            g = gen_h[j]
+            g = gen_h[j] if gen_h is not None else host_out[i, :, :gen.shape[-1]]
             if tts:
                 g = g[:, results[i][2][0][1] * 320:]
             out_host[i] = g

@@ -98,3 +98,30 @@ def test_inference_batch_host_buffers(stack):
         assert o.shape == (1, res.shape[-1] * 320) and torch.equal(o, a)          # seed-deterministic end to end
         assert marks.shape[-1] == res.shape[-1]
     assert tm["gen_frames"] > 0 and tm["lm_ms"] > 0
+
+
+def test_inference_batch_pinned_result_buffer_and_device_splice(stack):
+    """host_out (a pinned buffer the caller reuses) must give the same waveforms as the default path, and the device-side
+    splice of the watermark decoder's new_wav must equal the host one (inference_scale.py:66-78) on every span geometry."""
+    cfg, sd, model, ccfg, csd, tok = stack
+    g = torch.Generator().manual_seed(5)
+    wavs = [0.1 * torch.randn(1, 9600, generator=g) for _ in range(3)]
+    texts = [torch.randint(0, cfg.text_vocab_size, (n,), generator=g) for n in (6, 9, 7)]
+    spans = [[[30, 30]], [[0, 4]], [[5, 12], [20, 30]]]
+    torch.manual_seed(0)
+    want, results = pipeline.inference_batch(model, tok, wavs, texts, spans, DC, cfg_coef=1.5, cfg_stride=2, aug_text=True,
+                                             use_watermark=True, tts=False, seed=78)
+    longest = max(r[0].shape[-1] for r in results) * 320
+    host_out = torch.empty(3, 1, longest + 640).pin_memory()
+    torch.manual_seed(0)
+    got, _ = pipeline.inference_batch(model, tok, [w.pin_memory() for w in wavs], texts, spans, DC, cfg_coef=1.5, cfg_stride=2,
+                                      aug_text=True, use_watermark=True, tts=False, seed=78, host_out=host_out)
+    for a, b in zip(want, got):
+        assert a.shape == b.shape and torch.equal(a, b)
+        assert b.data_ptr() >= host_out.data_ptr() and b.data_ptr() < host_out.data_ptr() + host_out.numel() * 4
+    for w, (res, marks, masks, nmi) in zip(wavs, results):
+        n_frames = res.shape[-1]
+        ref = pipeline.splice_original(w, n_frames, masks, nmi)
+        dev = torch.zeros(1, n_frames * 320, device="cuda")
+        pipeline.splice_original_device(w.cuda(), dev, masks, nmi)
+        assert torch.equal(dev.cpu(), ref)
