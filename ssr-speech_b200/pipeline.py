@@ -109,7 +109,8 @@ def inference_batch(model, audio_tokenizer: AudioTokenizer, wavs: List[torch.Ten
         wav_dev[i].copy_(w.reshape(1, T).to(torch.float32), non_blocking=True)
     codes, scale, _ = audio_tokenizer.encode(wav_dev)                                 # [U,K,Tf]
     ev[1].record()
-    ys = [codes[i].transpose(0, 1) for i in range(U)]                                 # [Tf,K]
+    codes_h = codes.to("cpu")                                                         # ONE read-back: the prologue is host-side integer work
+    ys = [codes_h[i].transpose(0, 1) for i in range(U)]                               # [Tf,K]
     results = model.inference_batch(text_ids, ys, mask_intervals, top_k=decode_config["top_k"], top_p=decode_config["top_p"],
                                     temperature=decode_config["temperature"], stop_repetition=decode_config["stop_repetition"],
                                     silence_tokens=decode_config.get("silence_tokens", (1388, 1898, 131)), cfg_coef=cfg_coef,
