@@ -495,7 +495,7 @@ def main():
     if not args.no_batch_sweep and args.batch == 32 and world == 1:
         for B in (1, 8):
             try:
-                other[str(B)] = batch_point(B, model, tok, wavs, texts, spans, dc, args, gen_frames, wb, kv_per_pos, S0, n_iter, peak)
+                other[str(B)] = batch_point(B, model, tok, wavs, texts, spans, dc, args, gen_frames, wb, kv_per_pos, S0, n_iter, peak, host_out=host_out)
             except Exception as e:  # pragma: no cover
                 other[str(B)] = {"error": repr(e)}
 
@@ -570,12 +570,13 @@ def main():
         dist.destroy_process_group()
 
 
-def batch_point(B, model, tok, wavs, texts, spans, dc, args, gen_frames, wb, kv_per_pos, S0, n_iter, peak):
+def batch_point(B, model, tok, wavs, texts, spans, dc, args, gen_frames, wb, kv_per_pos, S0, n_iter, peak, host_out=None):
     """One point of BASELINE's batch sweep on this rank: 1 warm-up + 2 timed passes of the whole hot path (host buffers in,
     waveforms out) at batch B, with the decode loop's HBM roofline fraction at that batch."""
     from ssr_speech_b200 import pipeline
     run = lambda tm: pipeline.inference_batch(model, tok, wavs[:B], texts[:B], spans[:B], dc, cfg_coef=1.5, cfg_stride=5,
-                                              aug_text=True, use_watermark=not args.no_watermark, tts=True, seed=1000, timings=tm)
+                                              aug_text=True, use_watermark=not args.no_watermark, tts=True, seed=1000, timings=tm,
+                                              host_out=None if host_out is None else host_out[:B])
     run({})
     torch.cuda.synchronize()
     n, acc = 2, {}
@@ -604,6 +605,8 @@ def config_point(model, tok, cfg, args, wb, peak, B, T, lx, span, aug_text, top_
     Y0 = T + 10 for TTS and T + 10 - (b - a) for a one-span edit."""
     from ssr_speech_b200 import pipeline
     wavs, texts, _ = synth_inputs(B, T / 50.0, lx, rank=7)
+    wavs = [w.pin_memory() for w in wavs]
+    host_out = torch.empty(B, 1, (T + 10 * lx) * 320, dtype=torch.float32).pin_memory()
     tts = span is None
     spans = [[[T, T]] if tts else [list(span)]] * B
     dc = {"top_k": top_k, "top_p": top_p, "temperature": 1.0, "stop_repetition": stop_rep, "kvcache": 1, "codec_sr": 50,
@@ -611,7 +614,7 @@ def config_point(model, tok, cfg, args, wb, peak, B, T, lx, span, aug_text, top_
     y0 = T + 10 - (0 if tts else span[1] - span[0])
     gen_frames = 10 * lx - y0 + 1
     run = lambda tm: pipeline.inference_batch(model, tok, wavs, texts, spans, dc, cfg_coef=1.5, cfg_stride=5, aug_text=aug_text,
-                                              use_watermark=not args.no_watermark, tts=tts, seed=1000, timings=tm)
+                                              use_watermark=not args.no_watermark, tts=tts, seed=1000, timings=tm, host_out=host_out)
     tm0 = {}
     _, res = run(tm0)
     got = int(res[0][1].sum())
