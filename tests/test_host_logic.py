@@ -235,3 +235,26 @@ def test_max_n_spans_beyond_the_engine_state_is_rejected():
     ns.max_n_spans = 4
     with pytest.raises(AssertionError):
         SSRConfig.from_args(ns)
+
+
+@pytest.mark.parametrize("spans", [[[30, 30]], [[0, 4]], [[5, 12], [20, 30]], [[0, 3], [10, 10], [28, 30]]])
+def test_device_splice_of_the_watermark_input_equals_the_host_splice(spans):
+    """pipeline.splice_original_device (slice copies into a zeroed buffer, used on tensors that are already in HBM) against
+    pipeline.splice_original (inference_scale.py:66-78) on the masks / ori_masks seq.finalize produces for TTS, an edit at frame 0,
+    two spans and three spans with an empty one.  Runs on CPU tensors: the function is device-agnostic."""
+    from ssr_speech_b200 import pipeline
+    cfg = cfg_tiny()
+    rng = np.random.default_rng(len(spans))
+    T = 30
+    y = rng.integers(0, cfg.audio_vocab_size, size=(cfg.n_codebooks, T))
+    prep = seq.prepare(cfg, y, spans)
+    gen = [rng.integers(0, cfg.audio_vocab_size, size=(int(rng.integers(3, 9)) + cfg.n_codebooks, cfg.n_codebooks)) for _ in range(prep.num_spans)]
+    res, marks, masks, nmi = seq.finalize(cfg, prep, gen)
+    n_frames = res.shape[-1]
+    wav = torch.from_numpy(rng.standard_normal((1, T * 320)).astype(np.float32))
+    want = pipeline.splice_original(wav, n_frames, masks, nmi)
+    got = torch.zeros(1, n_frames * 320)
+    pipeline.splice_original_device(wav, got, masks, nmi)
+    assert torch.equal(got, want)
+    kept = int((np.asarray(marks).reshape(-1) == 0).sum())
+    assert int((want != 0).sum()) <= kept * 320
