@@ -210,7 +210,7 @@ int gemm_tc(const GemmArgs& g, void* workspace, size_t workspace_bytes, cudaStre
 size_t gemm_tc_workspace_bytes(int max_rows_decode, int max_n);
 bool gemm_tc_supported(const GemmArgs& g);
 
-// ---- prefill GEMM on CTA pairs (gemm_flat2.cu; experimental, SSRB_FLAT_2CTA=1): tcgen05.mma.cta_group::2, 256 x 256 tiles --------
+// ---- prefill GEMM on CTA pairs (gemm_flat2.cu; the default since round 2, SSRB_FLAT_2CTA=0 opts out): tcgen05.mma.cta_group::2, 256 x 256 tiles
 bool gemm_flat2_enabled();
 bool gemm_flat2_supported(const GemmArgs& g);
 int gemm_flat2(const GemmArgs& g, cudaStream_t stream);

@@ -1,5 +1,6 @@
 #!/bin/bash
-# Round-2 bring-up of the two experimental kernels on one B200 (both off by default, neither has run on hardware yet):
+# Bring-up / A/B of the persistent layer kernel and the CTA-pair prefill GEMM on one B200 (results: profiles/r02a_summary.md — the
+# layer kernel lost and stays off, the CTA-pair GEMM won and is the default):
 #   A. persistent per-layer decode GEMM kernel (csrc/gemm_layer.cu, SSRB_LAYER_KERNEL=1)
 #   B. CTA-pair prefill GEMM (csrc/gemm_flat2.cu, SSRB_FLAT_2CTA=1)
 # For each: the gated parity tests first (every case in a child process under a timeout; the kernels' spins trap after 2 s, so a
