@@ -28,9 +28,14 @@ namespace ssrb {
 
 namespace {
 
-constexpr int AT_SUB = 64, AT_ROWB = 256, AT_STAGES = 3;            // keys per tile, bytes per key row
+#ifndef AT_SUB_KEYS
+#define AT_SUB_KEYS 64         // keys per tile and ring depth (A/B'd: 64 x 3 against 32 x 6, profiles/r02d_summary.md)
+#define AT_NSTAGES 3
+#endif
+constexpr int AT_SUB = AT_SUB_KEYS, AT_ROWB = 256, AT_STAGES = AT_NSTAGES;            // keys per tile, bytes per key row
+constexpr int AT_JP = AT_SUB / 16;                                  // key pairs per consumer warp and tile
 constexpr int AT_STAGE_BYTES = 2 * AT_SUB * AT_ROWB;                // K + V
-constexpr int AT_SMEM = AT_STAGES * AT_STAGE_BYTES + 64;
+constexpr int AT_SMEM = AT_STAGES * AT_STAGE_BYTES + 16 * AT_STAGES + 16;
 constexpr int AT_CW = 8;                                            // consumer warps
 constexpr int AT_THREADS = (AT_CW + 1) * 32;
 constexpr int AT_MAXR = 1024;                                       // rows per launch (prefix table in shared memory)
@@ -116,10 +121,10 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_decode_tma_kernel(const fl
         const int n_old = seq_len[r];
         s_pref[r + 1] = st[r / rpu].done ? 0 : max(1, (n_old + AT_SUB - 1) / AT_SUB);
     }
-    const uint32_t ring = smem_u32(smem), bar0 = ring + AT_STAGES * AT_STAGE_BYTES;   // full[s] = bar0+8s, empty[s] = bar0+24+8s
+    const uint32_t ring = smem_u32(smem), bar0 = ring + AT_STAGES * AT_STAGE_BYTES;   // full[s] = bar0+8s, empty[s] = bar0+8*AT_STAGES+8s
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < AT_STAGES; s++) { mbar_init(bar0 + 8 * s, 1); mbar_init(bar0 + 24 + 8 * s, AT_CW); }
+        for (int s = 0; s < AT_STAGES; s++) { mbar_init(bar0 + 8 * s, 1); mbar_init(bar0 + 8 * AT_STAGES + 8 * s, AT_CW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -152,7 +157,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_decode_tma_kernel(const fl
             for (int i = 0; i < g1 - g0; i++) {
                 const int s = i % AT_STAGES;
                 const uint32_t ph = (i / AT_STAGES) & 1;
-                mbar_wait(bar0 + 24 + 8 * s, ph ^ 1);
+                mbar_wait(bar0 + 8 * AT_STAGES + 8 * s, ph ^ 1);
                 const int k0 = p.t * AT_SUB;
                 const int nk = min(AT_SUB, n_old - k0);
                 if (nk > 0) {
@@ -219,11 +224,11 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_decode_tma_kernel(const fl
             const int nk = min(AT_SUB, n_old - t * AT_SUB);
             mbar_wait(bar0 + 8 * s, ph);
             const uint32_t kt = ring + s * AT_STAGE_BYTES + dl * 2, vt = kt + AT_SUB * AT_ROWB;
-            float sc[4];
+            float sc[AT_JP];
             float mnew = mrun;
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int kl = warp * 8 + j * 2 + half;
+            for (int j = 0; j < AT_JP; j++) {
+                const int kl = warp * (AT_SUB / AT_CW) + j * 2 + half;
                 float kk[8];
                 lds8_bf16(kt + kl * AT_ROWB, kk);
                 float pk = 0.f;
@@ -242,8 +247,8 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_decode_tma_kernel(const fl
 #pragma unroll
                 for (int e = 0; e < 8; e++) o[e] *= corr;
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const int kl = warp * 8 + j * 2 + half;
+                for (int j = 0; j < AT_JP; j++) {
+                    const int kl = warp * (AT_SUB / AT_CW) + j * 2 + half;
                     if (kl < nk) {
                         float vv[8];
                         lds8_bf16(vt + kl * AT_ROWB, vv);
@@ -256,7 +261,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_decode_tma_kernel(const fl
                 mrun = mnew;
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar0 + 24 + 8 * s);     // this warp is done with the stage
+            if (lane == 0) mbar_arrive(bar0 + 8 * AT_STAGES + 8 * s);     // this warp is done with the stage
         }
         // ---- end of the piece: merge the 16 (warp, half) partial states (named barrier: the producer warp is elsewhere)
         const int slot = warp * 2 + half;
