@@ -2,7 +2,8 @@
 
 Brought up and A/B'd on a B200 in round 2 (profiles/r02a_summary.md): correct, but its three grid barriers cost as much as the
 kernel boundaries they replace (decode iteration 1.79 -> 1.95 ms), so the per-GEMM chain stays the product path and the kernel
-stays off by default; these tests run only with SSRB_EXPERIMENTAL=1 (tools/gpu_layer_ab.sh sets it).
+stays off by default.  The tests are part of the default GPU run (green on two boxes in round 2); the file sorts last so that a
+problem in this off-path kernel cannot hide product tests behind `pytest -x`.
 Every case runs in a child process under a timeout: a bug in a grid barrier shows up as a hang, and a hung kernel dies with
 its process.
 
@@ -20,9 +21,7 @@ import pytest
 
 from conftest import ROOT
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("SSRB_EXPERIMENTAL") != "1",
-                                 reason="experimental kernel, off the product path (set SSRB_EXPERIMENTAL=1)")]
+pytestmark = pytest.mark.gpu
 
 OP_SNIPPET = r"""
 import ctypes as C, json, os, sys

@@ -10,7 +10,7 @@ set -u
 mkdir -p gpurun_out
 SECTIONS=${SECTIONS:-"A B"}
 if [[ " $SECTIONS " == *" A "* ]]; then
-  SSRB_EXPERIMENTAL=1 timeout 1200 python -m pytest tests/test_gpu_layer_kernel.py -m gpu -x -q > gpurun_out/pytest_layer.log 2>&1
+  SSRB_EXPERIMENTAL=1 timeout 1200 python -m pytest tests/test_gpu_zz_layer_kernel.py -m gpu -x -q > gpurun_out/pytest_layer.log 2>&1
   rc=$?; echo "pytest rc=$rc" >> gpurun_out/pytest_layer.log
   tail -15 gpurun_out/pytest_layer.log
   if [ $rc -eq 0 ]; then bash tools/gpu_ab.sh base:SSRB_LAYER_KERNEL=0,TL=1 layer:SSRB_LAYER_KERNEL=1,TL=1

@@ -17,6 +17,6 @@ for tool in memcheck racecheck synccheck; do
 done
 if [ "${SSRB_EXPERIMENTAL:-0}" = "1" ]; then   # the experimental layer kernel: one small case under memcheck (watchdog raised: 50x slowdown)
   SSRB_NO_GRAPH=1 timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 \
-      python -m pytest "tests/test_gpu_layer_kernel.py::test_layer_kernel_matches_per_gemm_chain" -m gpu -x -q -k "M16-D512" > gpurun_out/sanitize_layer.log 2>&1
+      python -m pytest "tests/test_gpu_zz_layer_kernel.py::test_layer_kernel_matches_per_gemm_chain" -m gpu -x -q -k "M16-D512" > gpurun_out/sanitize_layer.log 2>&1
   echo "layer memcheck rc=$?" | tee -a gpurun_out/sanitize_layer.log
 fi
