@@ -13,9 +13,10 @@
 //     n = phase*Cout + co — one GEMM row holds the s output steps produced by input step i, which IS the channels-last
 //     layout of the output; the reference's trim (left = total - total//2) is an address offset plus a validity window.
 // The zero guards implement the reference's zero padding (pad_mode 'constant'); TMA walks the shifted rows directly.
-// Pipeline: TMA (3-D map {Cw, rows, batch}, 128B swizzle) -> 3-stage smem ring -> tcgen05.mma 128 x NT x 16 -> TMEM ->
-// epilogue (bias | per-mark bias, residual add, raw and/or ELU'd bf16 store).  ELU (seanet.py:39-46) is applied by the
-// PRODUCER's epilogue, so consumers read ready-made GEMM operands.
+// Pipeline (persistent CTAs, see conv_tc_kernel): TMA (3-D map {Cw, rows, batch}, 128B swizzle) -> 2-stage smem ring ->
+// tcgen05.mma 128 x NT x 16 -> two TMEM accumulators -> 8 epilogue warps (bias | per-mark bias, residual add, raw and/or ELU'd
+// bf16, staged through shared memory into whole-line stores).  ELU (seanet.py:39-46) is applied by the PRODUCER's epilogue,
+// so consumers read ready-made GEMM operands.
 #include <cuda.h>
 
 #include <mutex>
