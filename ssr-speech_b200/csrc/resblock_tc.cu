@@ -2,14 +2,14 @@
 //
 //        y = x + conv_k1( ELU( conv_k3( ELU(x) ) ) )                 audiocraft/modules/seanet.py:16-60 (true_skip, 1 residual layer)
 //
-// Per CTA: 128 time steps of one utterance, ALL channels.  The hidden activation h = ELU(conv_k3(ELU(x)) + b1) never leaves the SM:
+// Per tile: 128 time steps of one utterance, ALL channels (persistent CTAs walk the tile list).  The hidden activation h = ELU(conv_k3(ELU(x)) + b1) never leaves the SM:
 //   GEMM 1  [128 x 3C] . W1'^T -> acc1 [128 x C/2] in tensor memory     (three tap-GEMMs over row-shifted TMA views, as conv_tc.cu)
 //   epilogue 1: acc1 + b1 -> ELU -> bf16 -> shared memory, written directly in the K-major 128-byte-swizzled layout UMMA reads
 //   GEMM 2  h [128 x C/2] (shared memory) . W2^T -> acc2 [128 x C]      (W2 streamed through the same TMA ring)
 //   epilogue 2: acc2 + b2 + x (raw skip) -> raw and / or ELU'd bf16 channels-last stores
-// Against two conv_tc launches this removes the HBM round trip of h, one kernel boundary on the critical path and half of the
-// per-CTA fixed costs (barrier init, TMEM allocation, pipeline fill) that dominate these short-K layers (ncu: 4.7-30 % tensor
-// pipe active, profiles/r01e_ncu_full_conv_tc_codec.csv).
+// Against two conv_tc launches this removes the HBM round trip of h and one kernel boundary on the critical path; the persistent
+// tile loop pays barrier init / TMEM allocation / pipeline fill once per CTA instead of once per tile (they dominated these short-K
+// layers: ncu 9-18 % warps active with one tile per CTA, profiles/r02c_ncu_full_codec_kernels.csv).
 #include <cuda.h>
 
 #include <mutex>
