@@ -258,3 +258,19 @@ def test_device_splice_of_the_watermark_input_equals_the_host_splice(spans):
     assert torch.equal(got, want)
     kept = int((np.asarray(marks).reshape(-1) == 0).sum())
     assert int((want != 0).sum()) <= kept * 320
+
+
+def test_fast_elu_for_bf16_outputs_stays_inside_half_a_bf16_ulp():
+    """csrc/common.cuh elu1_bf16: x > 0 ? x : (x > -1e-3 ? x + x^2/2 : exp(x) - 1 through MUFU.EX2).  Restated in float32 with the
+    hardware approximation's worst-case relative error (2^-22 on exp2) injected, against expm1 in float64: the result must differ
+    by far less than half a bf16 ulp (2^-9 relative) everywhere, which is what makes it safe in front of a bf16 store."""
+    x = -np.logspace(-8, np.log10(30.0), 20000).astype(np.float32)
+    want = np.expm1(x.astype(np.float64))
+    series = (x + np.float32(0.5) * x * x).astype(np.float32)
+    worst = 0.0
+    for sign in (-1.0, 1.0):
+        ex = (np.exp(x.astype(np.float64)) * (1.0 + sign * 2.0 ** -22)).astype(np.float32)
+        got = np.where(x > np.float32(-1e-3), series, (ex - np.float32(1.0)).astype(np.float32)).astype(np.float64)
+        worst = max(worst, float(np.max(np.abs(got - want) / np.abs(want))))
+    assert worst < 2.0 ** -9 / 4, worst
+    assert worst < 5e-4, worst
