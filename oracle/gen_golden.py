@@ -232,13 +232,74 @@ def run_codec_cases():
     return rep
 
 
+def synth_train_batch(cfg, seed: int, lens=((9, 26), (12, 33), (7, 19))):
+    """A dataset-style training batch for SSR_Speech.forward (models/ssr.py:280-379): per utterance [kept prefix, <mts>, kept
+    suffix, <mts>, masked span, <eog>] in the delayed codebook pattern (codebook k shifted right by k, empty_token fill), padded
+    with audio_pad_token / text_pad_token to the batch maxima.  Exercises every token class the loss masks look at."""
+    g = torch.Generator().manual_seed(seed)
+    K, B = cfg.n_codebooks, len(lens)
+    xs, ys = [], []
+    for Lx, T in lens:
+        xs.append(torch.randint(0, cfg.text_vocab_size, (Lx,), generator=g))
+        a = int(torch.randint(2, T // 2, (1,), generator=g))
+        b = int(torch.randint(a + 2, T - 2, (1,), generator=g))
+        tok = torch.randint(0, cfg.audio_vocab_size, (K, T), generator=g)
+        mts = torch.full((K, 1), cfg.mts, dtype=torch.long)
+        segs = [tok[:, :a], mts, tok[:, b:], mts, torch.cat([tok[:, a:b], torch.full((K, 1), cfg.eog, dtype=torch.long)], 1)]
+        flat = torch.cat(segs, 1)
+        L = flat.shape[1] + K - 1
+        y = torch.full((K, L), cfg.empty_token, dtype=torch.long)
+        for k in range(K):
+            y[k, k:k + flat.shape[1]] = flat[k]
+        ys.append(y)
+    x_lens = torch.tensor([x.shape[0] for x in xs])
+    y_lens = torch.tensor([y.shape[1] for y in ys])
+    x = torch.full((B, int(x_lens.max())), cfg.text_pad_token, dtype=torch.long)
+    y = torch.full((B, K, int(y_lens.max())), cfg.audio_pad_token, dtype=torch.long)
+    for i in range(B):
+        x[i, :x_lens[i]] = xs[i]
+        y[i, :, :y_lens[i]] = ys[i]
+    return x, x_lens, y, y_lens
+
+
+def run_train_forward_cases():
+    """the unmodified reference's training forward (eval mode: dropout inactive) on a synthetic batch, for both
+    settings of the loss-mask switches; the oracle's forward_loss on the same batch; fixtures for the CPU and GPU tests."""
+    ssr = ref_loader.load_reference_ssr()
+    cfg = cfg_tiny()
+    sd = make_lm_state_dict(cfg, seed=7)
+    ns = cfg.to_namespace()
+    model = ssr.SSR_Speech(ns).eval()
+    model.load_state_dict(sd, strict=True)
+    oracle = LMOracle(cfg, sd)
+    out = {}
+    for tag, (pmt, pall, cw) in {"default": (1, 0, "[5,1,0.5,0.1]"), "all": (0, 1, None)}.items():
+        x, x_lens, y, y_lens = synth_train_batch(cfg, seed=41)
+        model.args.predict_mask_token, model.args.predict_all, model.args.codebook_weight = pmt, pall, cw
+        with torch.no_grad():
+            ref = model({"x": x, "x_lens": x_lens, "y": y, "y_lens": y_lens})
+        got = oracle.forward_loss(x, x_lens, y, y_lens, predict_mask_token=bool(pmt), predict_all=bool(pall),
+                                  codebook_weight=None if cw is None else eval(cw))
+        rl, rt, rn = float(ref["loss"]), float(ref["top10acc"]), int(ref["effective_ntoken"])
+        rb = [float(v) for v in ref["top10acc_by_codebook"]]
+        print(f"[train] {tag:<8} reference loss {rl:.6f} top10acc {rt:.4f} ntoken {rn} | oracle loss {got['loss']:.6f} "
+              f"top10acc {got['top10acc']:.4f} ntoken {got['effective_ntoken']} | rel.err {abs(got['loss'] - rl) / abs(rl):.2e}")
+        out.update({f"{tag}_loss": rl, f"{tag}_top10acc": rt, f"{tag}_ntoken": rn, f"{tag}_top10acc_by_codebook": np.asarray(rb),
+                    f"{tag}_predict_mask_token": pmt, f"{tag}_predict_all": pall,
+                    f"{tag}_codebook_weight": np.asarray(eval(cw) if cw else [1.0] * cfg.n_codebooks, dtype=np.float64)})
+    np.savez_compressed(os.path.join(GOLD, "lm_train_forward.npz"), x=x.numpy(), x_lens=x_lens.numpy(), y=y.numpy(),
+                        y_lens=y_lens.numpy(), weights_seed=7, **out)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(8)
-    which = sys.argv[1] if len(sys.argv) > 1 else "all"       # all | lm | codec | lm:<case>,<case> (only those fixtures)
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"       # all | lm | codec | train | lm:<case>,<case> (only those fixtures)
     if which.startswith("lm:"):
         run_lm_cases(only=set(which[3:].split(",")))
     if which in ("all", "lm"):
         run_lm_cases()
     if which in ("all", "codec"):
         run_codec_cases()
+    if which in ("all", "train"):
+        run_train_forward_cases()

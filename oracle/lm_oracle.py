@@ -163,6 +163,54 @@ class LMOracle:
         h = h[x.shape[0]:]
         return torch.stack([self.heads(h[t]) for t in range(h.shape[0])], 0)
 
+    # -- training forward / loss ------------------------------------------------------
+    @staticmethod
+    def loss_masks(cfg, y: torch.Tensor, predict_mask_token: bool = True, predict_all: bool = False):
+        """models/ssr.py:333-347 on one utterance's y [K, T] (already cut to its length): the targets are y shifted by one,
+        `mask` counts a target unless it is audio_pad / empty (and, without predict_mask_token, a mask token); `tmp_mask`
+        additionally drops everything BEFORE each occurrence of the first mask-token id (`mts`) unless predict_all.
+        Returns (targets [K, T-1], mask, tmp_mask)."""
+        tg = y[:, 1:]
+        mask = (tg != cfg.audio_pad_token) & (tg != cfg.empty_token)
+        if not predict_mask_token:
+            mask = mask & (tg < cfg.mts)
+        tmp = mask.clone()
+        if not predict_all:
+            for k, t in (tg == cfg.mts).nonzero(as_tuple=False).tolist():
+                tmp[k, :t] = False
+        return tg, mask, tmp
+
+    @torch.no_grad()
+    def forward_loss(self, x: torch.Tensor, x_lens: torch.Tensor, y: torch.Tensor, y_lens: torch.Tensor,
+                     predict_mask_token: bool = True, predict_all: bool = False, codebook_weight=None):
+        """SSR_Speech.forward (models/ssr.py:280-379) in eval mode: x [B, S] int64, y [B, K, T] int64 (dataset-prepared: mask
+        tokens, eog, audio_pad padding), lengths [B].  Padded positions are masked as keys in the reference, so every utterance
+        is run at its own length.  Returns the reference's dict: loss = sum_k mean-CE_k * ntokens_k * weight_k, top10acc,
+        top10acc_by_codebook, effective_ntoken."""
+        cfg = self.cfg
+        K = cfg.n_codebooks
+        B = x.shape[0]
+        nll = [[] for _ in range(K)]
+        hit = [[] for _ in range(K)]
+        ntok = [0] * K
+        for b in range(B):
+            xl, yl = int(x_lens[b]), int(y_lens[b])
+            yb = y[b, :, :yl]
+            logits = self.teacher_forced_logits(x[b, :xl], yb)[:-1].to(torch.float64)          # [T-1, K, V]
+            tg, mask, tmp = self.loss_masks(cfg, yb, predict_mask_token, predict_all)
+            for k in range(K):
+                lk, tk = logits[:, k][tmp[k]], tg[k][tmp[k]]
+                nll[k].append(F.cross_entropy(lk, tk, reduction="none"))
+                hit[k].append((lk.topk(10, dim=-1).indices == tk[:, None]).any(-1))
+                ntok[k] += int(mask[k].sum())
+        cw = [1.0] * K if codebook_weight is None else list(codebook_weight)
+        loss_k = [torch.cat(nll[k]).mean() for k in range(K)]
+        acc_k = [torch.cat(hit[k]).double().mean() for k in range(K)]
+        by_cb = [float(acc_k[k]) * ntok[k] for k in range(K)]
+        return {"loss": float(sum(float(loss_k[k]) * ntok[k] * cw[k] for k in range(K))), "top10acc": float(sum(by_cb)),
+                "top10acc_by_codebook": by_cb, "effective_ntoken": int(sum(ntok)),
+                "loss_by_codebook": [float(v) for v in loss_k], "ntokens_by_codebook": ntok}
+
     # -- the decode loop ----------------------------------------------------------------------------
     @torch.no_grad()
     def inference(self, x: torch.Tensor, prompt_tokens: torch.Tensor, num_spans: int,

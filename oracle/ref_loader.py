@@ -41,8 +41,18 @@ def _stub_torchmetrics():
     import torch.nn as nn
 
     class MulticlassAccuracy(nn.Module):  # train-time metric only (models/ssr.py:12,181-189)
-        def __init__(self, *a, **k):
+        """Functional stand-in for torchmetrics.classification.MulticlassAccuracy as SSR_Speech.forward uses it
+        (top_k=10, average="micro", multidim_average="global", ignore_index=None on [N, C] logits and [N] targets):
+        the fraction of samples whose target is among the top_k scores."""
+
+        def __init__(self, num_classes=None, top_k=1, average="micro", **k):
             super().__init__()
+            assert average == "micro"
+            self.top_k = int(top_k)
+
+        def forward(self, preds, target):
+            top = preds.topk(self.top_k, dim=-1).indices
+            return (top == target[:, None]).any(-1).float().mean()
 
     tm = types.ModuleType("torchmetrics")
     tmc = types.ModuleType("torchmetrics.classification")

@@ -137,3 +137,19 @@ def test_iteration_bound_covers_the_reference_rollouts(gold_dir, name):
     assert total <= bound, (total, bound)
     if prep.num_spans == 1 and g["ref_span_tokens"][-cfg.n_codebooks, 0] == cfg.eog and total == bound:
         assert g["ref_span_lens"][0] == seq.expected_steps(cfg, len(x), prep.prompt_tokens.shape[1])
+
+
+@pytest.mark.parametrize("tag", ["default", "all"])
+def test_lm_oracle_reproduces_reference_training_forward(lm_oracle, gold_dir, tag):
+    """SSR_Speech.forward (models/ssr.py:280-379, eval mode) of the unmodified reference on a dataset-style batch
+    (mask tokens, eog, empty-token delay pattern, padding) for both settings of predict_mask_token / predict_all: loss,
+    top-10 accuracy (sum over codebooks of accuracy x ntokens) and effective_ntoken."""
+    cfg, oracle = lm_oracle
+    g = np.load(os.path.join(gold_dir, "lm_train_forward.npz"))
+    got = oracle.forward_loss(torch.from_numpy(g["x"]), torch.from_numpy(g["x_lens"]), torch.from_numpy(g["y"]),
+                              torch.from_numpy(g["y_lens"]), predict_mask_token=bool(g[f"{tag}_predict_mask_token"]),
+                              predict_all=bool(g[f"{tag}_predict_all"]), codebook_weight=g[f"{tag}_codebook_weight"].tolist())
+    assert got["effective_ntoken"] == int(g[f"{tag}_ntoken"])
+    assert abs(got["loss"] - float(g[f"{tag}_loss"])) <= 1e-5 * abs(float(g[f"{tag}_loss"]))
+    assert abs(got["top10acc"] - float(g[f"{tag}_top10acc"])) <= 1e-4
+    assert np.allclose(got["top10acc_by_codebook"], g[f"{tag}_top10acc_by_codebook"], atol=1e-4)
