@@ -144,6 +144,15 @@ int ssrb_lm_read_logits(ssrb_lm* lm, void* stream, float* host_out);
 int ssrb_lm_teacher_forced(ssrb_lm* lm, const int32_t* text, int Lx, const int32_t* audio, int Ty,
                            float* host_logits, void* stream);
 
+/* Training forward / loss of ONE utterance at its own length (replaces SSR_Speech.forward, models/ssr.py:280-379, in eval mode;
+ * the reference masks padded key positions, so a padded batch is the sum over its utterances): text[Lx], audio tokens
+ * [n_codebooks, Ty] as the dataset prepared them (mask tokens, eog, empty-token delay pattern), flags [n_codebooks, Ty-1] for the
+ * targets audio[:, 1:] — bit 0: the position enters the cross entropy / top-10 accuracy (tmp_masks, ssr.py:339-345), bit 1: it
+ * counts as a token (masks, ssr.py:333-337).  out [n_codebooks][4] (host, double): sum of -log p(target), positions in the loss,
+ * top-10 hits, token count.  Forward through the prefill path, fused masked cross entropy on the device.  Synchronises. */
+int ssrb_lm_forward_loss(ssrb_lm* lm, const int32_t* text, int Lx, const int32_t* audio, int Ty, const uint8_t* flags,
+                         double* out, void* stream);
+
 /* algorithmic HBM bytes of one decode iteration for the current batch state:
  * weights streamed once + KV read for every active row + KV written.  Synchronises. */
 int ssrb_lm_step_bytes(ssrb_lm* lm, void* stream, double* weight_bytes, double* kv_bytes);

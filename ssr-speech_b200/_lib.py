@@ -43,7 +43,7 @@ class CodecConfigC(C.Structure):
 EXPORTS = [
     "ssrb_last_error", "ssrb_version", "ssrb_launch_count",
     "ssrb_lm_create", "ssrb_lm_destroy", "ssrb_lm_load_tensor", "ssrb_lm_check_loaded", "ssrb_lm_begin",
-    "ssrb_lm_decode", "ssrb_lm_poll", "ssrb_lm_admit", "ssrb_lm_poll_flags", "ssrb_lm_read_tokens", "ssrb_lm_read_logits", "ssrb_lm_decode_path", "ssrb_lm_teacher_forced",
+    "ssrb_lm_decode", "ssrb_lm_poll", "ssrb_lm_admit", "ssrb_lm_poll_flags", "ssrb_lm_read_tokens", "ssrb_lm_read_logits", "ssrb_lm_decode_path", "ssrb_lm_teacher_forced", "ssrb_lm_forward_loss",
     "ssrb_lm_step_bytes", "ssrb_lm_profile_steps",
     "ssrb_codec_create", "ssrb_codec_destroy", "ssrb_codec_load_tensor", "ssrb_codec_check_loaded",
     "ssrb_codec_encode", "ssrb_codec_quantize", "ssrb_codec_decode", "ssrb_codec_wmdecode", "ssrb_codec_detect_watermark",
@@ -80,6 +80,7 @@ def load():
     lib.ssrb_lm_read_logits.argtypes = [vp, vp, vp]
     lib.ssrb_lm_decode_path.argtypes = [vp]
     lib.ssrb_lm_teacher_forced.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, vp]
+    lib.ssrb_lm_forward_loss.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, vp, vp]
     lib.ssrb_lm_step_bytes.argtypes = [vp, vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.ssrb_lm_profile_steps.argtypes = [vp, C.c_int, vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.ssrb_codec_create.argtypes = [C.POINTER(CodecConfigC), C.c_int, C.POINTER(vp)]

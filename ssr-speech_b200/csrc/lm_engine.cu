@@ -832,12 +832,9 @@ int ssrb_lm_read_logits(ssrb_lm* lm, void* stream, float* host_out) {
     return 0;
 }
 
-int ssrb_lm_teacher_forced(ssrb_lm* lm, const int32_t* text, int Lx, const int32_t* audio, int Ty, float* host_logits,
-                           void* stream) {
-    SSRB_CHECK(lm && text && audio && host_logits, "null argument");
-    SSRB_CUDA(cudaSetDevice(lm->device));
-    SSRB_TRY(ssrb_lm_check_loaded(lm));
-    cudaStream_t s = (cudaStream_t)stream;
+// teacher forcing through the prefill path: logits [Ty, K, V] fp32 for every audio position, left on the device (*lg_out, to be
+// cudaFree'd by the caller)
+static int teacher_forced_device(ssrb_lm* lm, const int32_t* text, int Lx, const int32_t* audio, int Ty, cudaStream_t s, float** lg_out) {
     SSRB_CHECK(Lx + Ty <= lm->cfg.max_prefill_tokens && Lx + Ty <= lm->cfg.max_seq, "sequence too long for teacher forcing");
     SSRB_CHECK(Ty <= lm->n_pos && Lx <= lm->n_pos, "PE table too small");
     ssrb_lm_batch b{};
@@ -856,12 +853,59 @@ int ssrb_lm_teacher_forced(ssrb_lm* lm, const int32_t* text, int Lx, const int32
     SSRB_CUDA(cudaMemcpyAsync(idx, hidx.data(), Ty * 4, cudaMemcpyHostToDevice, s));
     SSRB_CUDA(cudaStreamSynchronize(s));
     int rc = run_heads(lm, idx, Ty, hl, hhb, lg, s);
+    if (!rc && cudaStreamSynchronize(s) != cudaSuccess) { set_error("teacher forcing: heads failed"); rc = 1; }
+    cudaFree(hl); cudaFree(hhb); cudaFree(idx);
+    if (rc) { cudaFree(lg); return rc; }
+    *lg_out = lg;
+    return 0;
+}
+
+int ssrb_lm_teacher_forced(ssrb_lm* lm, const int32_t* text, int Lx, const int32_t* audio, int Ty, float* host_logits,
+                           void* stream) {
+    SSRB_CHECK(lm && text && audio && host_logits, "null argument");
+    SSRB_CUDA(cudaSetDevice(lm->device));
+    SSRB_TRY(ssrb_lm_check_loaded(lm));
+    cudaStream_t s = (cudaStream_t)stream;
+    float* lg = nullptr;
+    SSRB_TRY(teacher_forced_device(lm, text, Lx, audio, Ty, s, &lg));
+    int rc = 0;
+    cudaError_t ce = cudaMemcpyAsync(host_logits, lg, (size_t)Ty * lm->K * lm->V * 4, cudaMemcpyDeviceToHost, s);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+    if (ce != cudaSuccess) { set_error(cudaGetErrorString(ce)); rc = 1; }
+    cudaFree(lg);
+    return rc;
+}
+
+// SSR_Speech.forward of ONE utterance at its own length (models/ssr.py:280-379; padded key positions are masked in the reference,
+// so a batch is the sum over its utterances): forward over [text ; audio], heads on every audio position, then the masked
+// per-codebook cross entropy / top-10 accuracy on the device.  out [K][4] = {sum of nll, positions in the loss, top-10 hits,
+// token count}; the wrapper combines utterances and codebooks as ssr.py:352-372 does.
+int ssrb_lm_forward_loss(ssrb_lm* lm, const int32_t* text, int Lx, const int32_t* audio, int Ty, const uint8_t* flags, double* out,
+                         void* stream) {
+    SSRB_CHECK(lm && text && audio && flags && out, "null argument");
+    SSRB_CHECK(Ty >= 2, "forward_loss: at least two audio positions");
+    SSRB_CUDA(cudaSetDevice(lm->device));
+    SSRB_TRY(ssrb_lm_check_loaded(lm));
+    cudaStream_t s = (cudaStream_t)stream;
+    const int K = lm->K, V = lm->V, n = Ty - 1;
+    for (size_t i = 0; i < (size_t)K * Ty; i++) SSRB_CHECK(audio[i] >= 0 && audio[i] < V, "forward_loss: audio token outside the embedding table");
+    float* lg = nullptr;
+    SSRB_TRY(teacher_forced_device(lm, text, Lx, audio, Ty, s, &lg));
+    int* d_aud = nullptr; unsigned char *d_flags = nullptr, *d_hit = nullptr; float* d_nll = nullptr; double* d_out = nullptr;
+    int rc = dev_alloc((void**)&d_aud, (size_t)K * Ty * 4) || dev_alloc((void**)&d_flags, (size_t)K * n) || dev_alloc((void**)&d_hit, (size_t)K * n) ||
+             dev_alloc((void**)&d_nll, (size_t)K * n * 4) || dev_alloc((void**)&d_out, (size_t)K * 4 * 8);
     if (!rc) {
-        cudaError_t ce = cudaMemcpyAsync(host_logits, lg, (size_t)Ty * K * V * 4, cudaMemcpyDeviceToHost, s);
+        cudaError_t ce = cudaMemcpyAsync(d_aud, audio, (size_t)K * Ty * 4, cudaMemcpyHostToDevice, s);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_flags, flags, (size_t)K * n, cudaMemcpyHostToDevice, s);
+        if (ce != cudaSuccess) { set_error(cudaGetErrorString(ce)); rc = 1; }
+    }
+    if (!rc) rc = launch_masked_ce(lg, d_aud, d_flags, Ty, K, V, d_nll, d_hit, d_out, s);
+    if (!rc) {
+        cudaError_t ce = cudaMemcpyAsync(out, d_out, (size_t)K * 4 * 8, cudaMemcpyDeviceToHost, s);
         if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
         if (ce != cudaSuccess) { set_error(cudaGetErrorString(ce)); rc = 1; }
     }
-    cudaFree(hl); cudaFree(hhb); cudaFree(lg); cudaFree(idx);
+    cudaFree(lg); cudaFree(d_aud); cudaFree(d_flags); cudaFree(d_hit); cudaFree(d_nll); cudaFree(d_out);
     return rc;
 }
 

@@ -838,6 +838,91 @@ __global__ void __launch_bounds__(SMP_T) sample_kernel(const float* __restrict__
     ts_end(ts);
 }
 
+// =================================================================================================
+// Training forward / loss (models/ssr.py:326-379): per-codebook masked cross entropy and top-10 accuracy of the
+// teacher-forced logits.  logits [Ty][K][V] fp32; the target of position t is the input token of position t+1 (ssr.py:330-331);
+// flags [K][Ty-1]: bit 0 = the position enters the loss / accuracy (tmp_mask), bit 1 = it counts as a token (mask).
+//   masked_ce_kernel        one CTA per (position, codebook): nll = logsumexp(l) - l[target]; hit = fewer than 10 logits exceed l[target]
+//   masked_ce_reduce_kernel one CTA per codebook: sums in a fixed order (double) -> {sum nll, n_loss, hits, n_tokens}
+// =================================================================================================
+__global__ void __launch_bounds__(256) masked_ce_kernel(const float* __restrict__ logits, const int* __restrict__ audio,
+                                                        const unsigned char* __restrict__ flags, int Ty, int K, int V,
+                                                        float* __restrict__ nll, unsigned char* __restrict__ hit) {
+    const int t = blockIdx.x, k = blockIdx.y, o = k * (Ty - 1) + t;
+    if (!(flags[o] & 1)) {
+        if (threadIdx.x == 0) { nll[o] = 0.f; hit[o] = 0; }
+        return;
+    }
+    __shared__ float red[8];
+    __shared__ int redi[8];
+    const int target = audio[k * Ty + t + 1];
+    const float* row = logits + ((size_t)t * K + k) * V;
+    const float lt = row[target];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float m = -INFINITY;
+    int above = 0;
+    for (int v = threadIdx.x; v < V; v += 256) {
+        const float l = row[v];
+        m = fmaxf(m, l);
+        above += l > lt ? 1 : 0;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+        above += __shfl_xor_sync(0xffffffffu, above, off);
+    }
+    if (lane == 0) { red[warp] = m; redi[warp] = above; }
+    __syncthreads();
+    m = red[0]; above = redi[0];
+#pragma unroll
+    for (int w = 1; w < 8; w++) { m = fmaxf(m, red[w]); above += redi[w]; }
+    __syncthreads();
+    float sum = 0.f;
+    for (int v = threadIdx.x; v < V; v += 256) sum += expf(row[v] - m);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+    if (lane == 0) red[warp] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tot = 0.f;
+        for (int w = 0; w < 8; w++) tot += red[w];                      // fixed order
+        nll[o] = (m + logf(tot)) - lt;
+        hit[o] = above < 10 ? 1 : 0;
+    }
+}
+
+__global__ void __launch_bounds__(256) masked_ce_reduce_kernel(const float* __restrict__ nll, const unsigned char* __restrict__ hit,
+                                                               const unsigned char* __restrict__ flags, int n, double* __restrict__ out) {
+    const int k = blockIdx.x;
+    __shared__ double s_l[256];
+    __shared__ int s_n[256], s_h[256], s_c[256];
+    double l = 0.0;
+    int nl = 0, nh = 0, nc = 0;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        const unsigned char f = flags[k * n + i];
+        if (f & 1) { l += (double)nll[k * n + i]; nl++; nh += hit[k * n + i]; }
+        if (f & 2) nc++;
+    }
+    s_l[threadIdx.x] = l; s_n[threadIdx.x] = nl; s_h[threadIdx.x] = nh; s_c[threadIdx.x] = nc;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (threadIdx.x < w) {
+            s_l[threadIdx.x] += s_l[threadIdx.x + w]; s_n[threadIdx.x] += s_n[threadIdx.x + w];
+            s_h[threadIdx.x] += s_h[threadIdx.x + w]; s_c[threadIdx.x] += s_c[threadIdx.x + w];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { out[k * 4 + 0] = s_l[0]; out[k * 4 + 1] = s_n[0]; out[k * 4 + 2] = s_h[0]; out[k * 4 + 3] = s_c[0]; }
+}
+
+int launch_masked_ce(const float* logits, const int* audio, const unsigned char* flags, int Ty, int K, int V, float* nll,
+                     unsigned char* hit, double* out, cudaStream_t s) {
+    SSRB_CHECK(Ty >= 2 && K >= 1 && V >= 10, "masked_ce: needs at least two positions and ten classes");
+    SSRB_LAUNCH(masked_ce_kernel, dim3(Ty - 1, K), 256, 0, s, logits, audio, flags, Ty, K, V, nll, hit);
+    SSRB_LAUNCH(masked_ce_reduce_kernel, K, 256, 0, s, nll, hit, flags, Ty - 1, out);
+    return 0;
+}
+
 int launch_sample(const float* logits, UttState* st, int* seq_len, int* next_tok, int* gen_tok, const float* noise,
                   int* iter_counter, const SampleParams& p_in, cudaStream_t s, int only_utt) {
     SampleParams p = p_in;

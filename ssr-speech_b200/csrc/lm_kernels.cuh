@@ -70,6 +70,9 @@ int launch_attn_prefill(const float* qkv, int D, int H, const void* kcache, cons
 int launch_attn_prefill_mma(const float* qkv, int D, int H, const void* kcache, const void* vcache, int Smax, int n_rows,
                             const int* row_ids, const int* row_start, const int* row_len, int max_len, void* out, cudaStream_t s);
 // CFG + logit rules + top-k/top-p + sample + state machine (models/ssr.py:690-754)
+// training forward / loss: masked per-codebook cross entropy + top-10 accuracy of teacher-forced logits (lm_kernels.cu)
+int launch_masked_ce(const float* logits, const int* audio, const unsigned char* flags, int Ty, int K, int V, float* nll,
+                     unsigned char* hit, double* out, cudaStream_t s);
 int launch_sample(const float* logits, UttState* st, int* seq_len, int* next_tok, int* gen_tok, const float* noise,
                   int* iter_counter, const SampleParams& p, cudaStream_t s, int only_utt = -1);
 

@@ -445,6 +445,71 @@ class SSR_Speech:
                                                           Ty, C.c_void_p(out.ctypes.data), _lib.stream_ptr()), "teacher_forced")
         return torch.from_numpy(out)
 
+    @torch.no_grad()
+    def forward(self, batch):
+        """Training forward / loss of the reference (models/ssr.py:280-379) in eval mode — forward only, no gradients:
+        batch = {"x" [B, S] int64, "x_lens" [B], "y" [B, K, T] int64 (dataset-prepared: mask tokens, eog, empty-token delay pattern,
+        audio_pad padding), "y_lens" [B]} -> {"loss", "top10acc", "top10acc_by_codebook", "effective_ntoken"} as the reference
+        returns them (loss = sum_k mean-CE_k * ntokens_k * codebook_weight_k).  The loss masks are integer logic on the host
+        (ssr.py:333-345); the transformer forward, the heads and the masked per-codebook cross entropy / top-10 accuracy run on
+        the device (ssrb_lm_forward_loss), one utterance at its own length — the reference masks padded keys, so this is the
+        same arithmetic."""
+        x, x_lens, y, y_lens = batch["x"], batch["x_lens"], batch["y"], batch["y_lens"]
+        if len(x) == 0:
+            return None
+        cfg, K = self.cfg, self.cfg.n_codebooks
+        assert x.ndim == 2, x.shape
+        assert x_lens.ndim == 1, x_lens.shape
+        assert y.ndim == 3 and y.shape[1] == K, y.shape
+        assert y_lens.ndim == 1, y_lens.shape
+        if self._device is None:
+            self.to("cuda")
+        a = self.args
+        predict_mask_token = bool(getattr(a, "predict_mask_token", 0))
+        predict_all = bool(getattr(a, "predict_all", 0))
+        cw = getattr(a, "codebook_weight", None)
+        cw = [1.0] * K if cw is None else [float(v) for v in (eval(cw) if isinstance(cw, str) else cw)]
+        xh = x.detach().to("cpu", torch.int64)
+        yh = y.detach().to("cpu", torch.int64)
+        Lmax, Tmax = int(x_lens.max()), int(y_lens.max())
+        self._ensure_engine(2, Lmax + Tmax + 8, Lmax + Tmax + 16, 8)
+        lib = _lib.load()
+        sums = np.zeros((K, 4), dtype=np.float64)
+        for b in range(xh.shape[0]):
+            xl, yl = int(x_lens[b]), int(y_lens[b])
+            xt = xh[b, :xl]
+            yb = yh[b, :, :yl]
+            if xt.numel() and (int(xt.min()) < 0 or int(xt.max()) >= cfg.n_text_tokens):
+                raise IndexError("index out of range in self (phoneme id outside the embedding table)")
+            tg = yb[:, 1:]
+            mask = (tg != cfg.audio_pad_token) & (tg != cfg.empty_token)                 # ssr.py:333-337
+            if not predict_mask_token:
+                mask = mask & (tg < cfg.mts)
+            tmp = mask.clone()
+            if not predict_all:                                                          # ssr.py:341-344
+                for k, t in (tg == cfg.mts).nonzero(as_tuple=False).tolist():
+                    tmp[k, :t] = False
+            flags = (tmp.to(torch.uint8) | (mask.to(torch.uint8) << 1)).contiguous().numpy()
+            xt32 = xt.to(torch.int32).contiguous().numpy()
+            yt32 = yb.to(torch.int32).contiguous().numpy()
+            out = np.zeros((K, 4), dtype=np.float64)
+            with torch.cuda.device(self._device):
+                _lib.check(lib.ssrb_lm_forward_loss(self._h, C.c_void_p(xt32.ctypes.data), xl, C.c_void_p(yt32.ctypes.data), yl,
+                                                    C.c_void_p(flags.ctypes.data), C.c_void_p(out.ctypes.data), _lib.stream_ptr()),
+                           "forward_loss")
+            sums += out
+        dev = self._device
+        loss_k = [sums[k, 0] / sums[k, 1] if sums[k, 1] > 0 else float("nan") for k in range(K)]       # mean over an empty set: nan, like F.cross_entropy
+        acc_k = [sums[k, 2] / sums[k, 1] if sums[k, 1] > 0 else float("nan") for k in range(K)]
+        nt = [int(sums[k, 3]) for k in range(K)]
+        by_cb = [torch.tensor(acc_k[k] * nt[k], dtype=torch.float32, device=dev) for k in range(K)]
+        return {"loss": torch.tensor(sum(loss_k[k] * nt[k] * cw[k] for k in range(K)), dtype=torch.float32, device=dev),
+                "top10acc": torch.tensor(sum(acc_k[k] * nt[k] for k in range(K)), dtype=torch.float32, device=dev),
+                "top10acc_by_codebook": by_cb,
+                "effective_ntoken": torch.tensor(sum(nt), device=dev)}
+
+    __call__ = forward
+
     def last_raw_logits(self) -> torch.Tensor:
         """[R, K, V] fp32 head outputs of the most recent iteration (before CFG / rules)."""
         K, V = self.cfg.n_codebooks, self.cfg.n_audio_tokens
