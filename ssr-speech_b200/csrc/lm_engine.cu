@@ -101,6 +101,7 @@ struct ssrb_lm {
     void *kcache = nullptr, *vcache = nullptr;
     size_t kv_layer_elems = 0;
     float* attn_ws = nullptr; int* tickets = nullptr;
+    char* tf_buf = nullptr; size_t tf_cap = 0;      // grow-only scratch of the teacher-forcing / training-loss entry points
     void* tc_ws = nullptr; size_t tc_ws_bytes = 0;
     PosDesc* d_desc = nullptr; int *d_rows = nullptr, *d_slots = nullptr;
     int *d_row_ids = nullptr, *d_row_start = nullptr, *d_row_len = nullptr, *d_last_idx = nullptr;
@@ -227,6 +228,7 @@ void ssrb_lm_destroy(ssrb_lm* lm) {
     cudaSetDevice(lm->device);
     cudaDeviceSynchronize();
     if (lm->graph) cudaGraphExecDestroy(lm->graph);
+    cudaFree(lm->tf_buf);
     for (auto& w : lm->layers) {
         void* ps[] = {w.wqkv, w.wo, w.w1, w.w2, w.bqkv, w.bo, w.b1, w.b2, w.ln1w, w.ln1b, w.ln2w, w.ln2b,
                       w.wqkv_f, w.w1_f, w.cqkv, w.bqkv_f, w.c1, w.b1_f};
@@ -832,11 +834,37 @@ int ssrb_lm_read_logits(ssrb_lm* lm, void* stream, float* host_out) {
     return 0;
 }
 
-// teacher forcing through the prefill path: logits [Ty, K, V] fp32 for every audio position, left on the device (*lg_out, to be
-// cudaFree'd by the caller)
-static int teacher_forced_device(ssrb_lm* lm, const int32_t* text, int Lx, const int32_t* audio, int Ty, cudaStream_t s, float** lg_out) {
+// grow-only scratch for the two entry points below (a cudaMalloc / cudaFree pair per buffer and call costs more than the forward
+// itself: measured 50 ms per 600-position utterance against 4.3 ms of kernels)
+static int tf_reserve(ssrb_lm* lm, size_t bytes) {
+    if (bytes <= lm->tf_cap) return 0;
+    if (lm->tf_buf) { SSRB_CUDA(cudaDeviceSynchronize()); cudaFree(lm->tf_buf); lm->tf_buf = nullptr; lm->tf_cap = 0; }
+    const size_t cap = bytes + bytes / 2;
+    SSRB_TRY(dev_alloc((void**)&lm->tf_buf, cap));
+    lm->tf_cap = cap;
+    return 0;
+}
+struct TfScratch { void* hl; void* hhb; float* lg; int* idx; int* aud; unsigned char* flags; unsigned char* hit; float* nll; double* out; };
+static int tf_carve(ssrb_lm* lm, int Ty, TfScratch* t) {
+    const size_t K = lm->K, V = lm->V, Hh = lm->Hh, D = lm->D, n = (size_t)Ty;
+    auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t sz[9] = {up(n * D * lm->esz), up(n * K * Hh * lm->esz), up(n * K * V * 4), up(n * 4), up(K * n * 4), up(K * n), up(K * n),
+                          up(K * n * 4), up(K * 4 * 8)};
+    size_t tot = 0;
+    for (size_t b : sz) tot += b;
+    SSRB_TRY(tf_reserve(lm, tot));
+    char* p = lm->tf_buf;
+    t->hl = p; p += sz[0]; t->hhb = p; p += sz[1]; t->lg = (float*)p; p += sz[2]; t->idx = (int*)p; p += sz[3];
+    t->aud = (int*)p; p += sz[4]; t->flags = (unsigned char*)p; p += sz[5]; t->hit = (unsigned char*)p; p += sz[6];
+    t->nll = (float*)p; p += sz[7]; t->out = (double*)p;
+    return 0;
+}
+
+// teacher forcing through the prefill path: logits [Ty, K, V] fp32 for every audio position, left on the device in t->lg
+static int teacher_forced_device(ssrb_lm* lm, const int32_t* text, int Lx, const int32_t* audio, int Ty, cudaStream_t s, TfScratch* t) {
     SSRB_CHECK(Lx + Ty <= lm->cfg.max_prefill_tokens && Lx + Ty <= lm->cfg.max_seq, "sequence too long for teacher forcing");
     SSRB_CHECK(Ty <= lm->n_pos && Lx <= lm->n_pos, "PE table too small");
+    SSRB_TRY(tf_carve(lm, Ty, t));
     ssrb_lm_batch b{};
     b.n_utt = 1; b.text = text; b.text_stride = Lx;
     std::vector<int> aud(audio, audio + (size_t)lm->K * Ty);
@@ -844,20 +872,11 @@ static int teacher_forced_device(ssrb_lm* lm, const int32_t* text, int Lx, const
     lm->rpu = 1;
     SSRB_TRY(prefill_chunk(lm, rows, &b, s, &aud));
     // heads over all audio positions
-    const int K = lm->K, V = lm->V, Hh = lm->Hh, D = lm->D;
-    void *hl = nullptr, *hhb = nullptr; float* lg = nullptr; int* idx = nullptr;
-    SSRB_TRY(dev_alloc(&hl, (size_t)Ty * D * lm->esz)); SSRB_TRY(dev_alloc(&hhb, (size_t)Ty * K * Hh * lm->esz));
-    SSRB_TRY(dev_alloc((void**)&lg, (size_t)Ty * K * V * 4)); SSRB_TRY(dev_alloc((void**)&idx, Ty * 4));
     std::vector<int> hidx(Ty);
     for (int i = 0; i < Ty; i++) hidx[i] = Lx + i;
-    SSRB_CUDA(cudaMemcpyAsync(idx, hidx.data(), Ty * 4, cudaMemcpyHostToDevice, s));
-    SSRB_CUDA(cudaStreamSynchronize(s));
-    int rc = run_heads(lm, idx, Ty, hl, hhb, lg, s);
-    if (!rc && cudaStreamSynchronize(s) != cudaSuccess) { set_error("teacher forcing: heads failed"); rc = 1; }
-    cudaFree(hl); cudaFree(hhb); cudaFree(idx);
-    if (rc) { cudaFree(lg); return rc; }
-    *lg_out = lg;
-    return 0;
+    SSRB_CUDA(cudaMemcpyAsync(t->idx, hidx.data(), Ty * 4, cudaMemcpyHostToDevice, s));
+    SSRB_CUDA(cudaStreamSynchronize(s));                   // hidx is a stack-lifetime host buffer
+    return run_heads(lm, t->idx, Ty, t->hl, t->hhb, t->lg, s);
 }
 
 int ssrb_lm_teacher_forced(ssrb_lm* lm, const int32_t* text, int Lx, const int32_t* audio, int Ty, float* host_logits,
@@ -866,14 +885,11 @@ int ssrb_lm_teacher_forced(ssrb_lm* lm, const int32_t* text, int Lx, const int32
     SSRB_CUDA(cudaSetDevice(lm->device));
     SSRB_TRY(ssrb_lm_check_loaded(lm));
     cudaStream_t s = (cudaStream_t)stream;
-    float* lg = nullptr;
-    SSRB_TRY(teacher_forced_device(lm, text, Lx, audio, Ty, s, &lg));
-    int rc = 0;
-    cudaError_t ce = cudaMemcpyAsync(host_logits, lg, (size_t)Ty * lm->K * lm->V * 4, cudaMemcpyDeviceToHost, s);
-    if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
-    if (ce != cudaSuccess) { set_error(cudaGetErrorString(ce)); rc = 1; }
-    cudaFree(lg);
-    return rc;
+    TfScratch t{};
+    SSRB_TRY(teacher_forced_device(lm, text, Lx, audio, Ty, s, &t));
+    SSRB_CUDA(cudaMemcpyAsync(host_logits, t.lg, (size_t)Ty * lm->K * lm->V * 4, cudaMemcpyDeviceToHost, s));
+    SSRB_CUDA(cudaStreamSynchronize(s));
+    return 0;
 }
 
 // SSR_Speech.forward of ONE utterance at its own length (models/ssr.py:280-379; padded key positions are masked in the reference,
@@ -889,24 +905,14 @@ int ssrb_lm_forward_loss(ssrb_lm* lm, const int32_t* text, int Lx, const int32_t
     cudaStream_t s = (cudaStream_t)stream;
     const int K = lm->K, V = lm->V, n = Ty - 1;
     for (size_t i = 0; i < (size_t)K * Ty; i++) SSRB_CHECK(audio[i] >= 0 && audio[i] < V, "forward_loss: audio token outside the embedding table");
-    float* lg = nullptr;
-    SSRB_TRY(teacher_forced_device(lm, text, Lx, audio, Ty, s, &lg));
-    int* d_aud = nullptr; unsigned char *d_flags = nullptr, *d_hit = nullptr; float* d_nll = nullptr; double* d_out = nullptr;
-    int rc = dev_alloc((void**)&d_aud, (size_t)K * Ty * 4) || dev_alloc((void**)&d_flags, (size_t)K * n) || dev_alloc((void**)&d_hit, (size_t)K * n) ||
-             dev_alloc((void**)&d_nll, (size_t)K * n * 4) || dev_alloc((void**)&d_out, (size_t)K * 4 * 8);
-    if (!rc) {
-        cudaError_t ce = cudaMemcpyAsync(d_aud, audio, (size_t)K * Ty * 4, cudaMemcpyHostToDevice, s);
-        if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_flags, flags, (size_t)K * n, cudaMemcpyHostToDevice, s);
-        if (ce != cudaSuccess) { set_error(cudaGetErrorString(ce)); rc = 1; }
-    }
-    if (!rc) rc = launch_masked_ce(lg, d_aud, d_flags, Ty, K, V, d_nll, d_hit, d_out, s);
-    if (!rc) {
-        cudaError_t ce = cudaMemcpyAsync(out, d_out, (size_t)K * 4 * 8, cudaMemcpyDeviceToHost, s);
-        if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
-        if (ce != cudaSuccess) { set_error(cudaGetErrorString(ce)); rc = 1; }
-    }
-    cudaFree(lg); cudaFree(d_aud); cudaFree(d_flags); cudaFree(d_hit); cudaFree(d_nll); cudaFree(d_out);
-    return rc;
+    TfScratch t{};
+    SSRB_TRY(teacher_forced_device(lm, text, Lx, audio, Ty, s, &t));
+    SSRB_CUDA(cudaMemcpyAsync(t.aud, audio, (size_t)K * Ty * 4, cudaMemcpyHostToDevice, s));
+    SSRB_CUDA(cudaMemcpyAsync(t.flags, flags, (size_t)K * n, cudaMemcpyHostToDevice, s));
+    SSRB_TRY(launch_masked_ce(t.lg, t.aud, t.flags, Ty, K, V, t.nll, t.hit, t.out, s));
+    SSRB_CUDA(cudaMemcpyAsync(out, t.out, (size_t)K * 4 * 8, cudaMemcpyDeviceToHost, s));
+    SSRB_CUDA(cudaStreamSynchronize(s));
+    return 0;
 }
 
 int ssrb_lm_step_bytes(ssrb_lm* lm, void* stream, double* weight_bytes, double* kv_bytes) {
