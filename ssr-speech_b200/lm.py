@@ -481,15 +481,7 @@ class SSR_Speech:
             yb = yh[b, :, :yl]
             if xt.numel() and (int(xt.min()) < 0 or int(xt.max()) >= cfg.n_text_tokens):
                 raise IndexError("index out of range in self (phoneme id outside the embedding table)")
-            tg = yb[:, 1:]
-            mask = (tg != cfg.audio_pad_token) & (tg != cfg.empty_token)                 # ssr.py:333-337
-            if not predict_mask_token:
-                mask = mask & (tg < cfg.mts)
-            tmp = mask.clone()
-            if not predict_all:                                                          # ssr.py:341-344
-                for k, t in (tg == cfg.mts).nonzero(as_tuple=False).tolist():
-                    tmp[k, :t] = False
-            flags = (tmp.to(torch.uint8) | (mask.to(torch.uint8) << 1)).contiguous().numpy()
+            flags = np.ascontiguousarray(seq.loss_flags(cfg, yb.numpy(), predict_mask_token, predict_all))     # ssr.py:333-345
             xt32 = xt.to(torch.int32).contiguous().numpy()
             yt32 = yb.to(torch.int32).contiguous().numpy()
             out = np.zeros((K, 4), dtype=np.float64)

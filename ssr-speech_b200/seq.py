@@ -129,3 +129,25 @@ def expected_steps(cfg: SSRConfig, x_len: int, prompt_len: int) -> int:
     y0 = prompt_len + 1                       # + <mts>
     j_star = max(10 * x_len - y0 + 1, 0) + 1  # iteration index (1-based) at which the guard fires
     return j_star + cfg.n_codebooks - 1
+
+
+def loss_flags(cfg: SSRConfig, y: np.ndarray, predict_mask_token: bool, predict_all: bool) -> np.ndarray:
+    """Loss masks of the training forward (reference models/ssr.py:330-345) for ONE utterance's dataset-prepared tokens y [K, T]
+    (cut to its length).  The targets are y[:, 1:]; returns uint8 flags [K, T-1]: bit 0 = the position enters the cross entropy
+    and the top-10 accuracy (`tmp_masks`), bit 1 = it counts as a token (`masks`).
+      masks     = target is neither audio_pad nor empty (and below `mts` unless predict_mask_token)
+      tmp_masks = masks, minus everything BEFORE each occurrence of the first mask-token id `mts` unless predict_all"""
+    tg = np.asarray(y)[:, 1:]
+    mask = (tg != cfg.audio_pad_token) & (tg != cfg.empty_token)
+    if not predict_mask_token:
+        mask &= tg < cfg.mts
+    tmp = mask.copy()
+    if not predict_all:
+        is_mts = tg == cfg.mts
+        # clearing [:t] for every occurrence t == clearing everything before the LAST occurrence in the row
+        has = is_mts.any(axis=1)
+        last = tg.shape[1] - 1 - np.argmax(is_mts[:, ::-1], axis=1)
+        cols = np.arange(tg.shape[1])[None, :]
+        tmp &= ~(has[:, None] & (cols < last[:, None]))
+    return (tmp.astype(np.uint8) | (mask.astype(np.uint8) << 1))
+

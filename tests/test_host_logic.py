@@ -274,3 +274,83 @@ def test_fast_elu_for_bf16_outputs_stays_inside_half_a_bf16_ulp():
         worst = max(worst, float(np.max(np.abs(got - want) / np.abs(want))))
     assert worst < 2.0 ** -9 / 4, worst
     assert worst < 5e-4, worst
+
+
+@pytest.mark.parametrize("predict_mask_token,predict_all", [(True, False), (False, False), (True, True), (False, True)])
+def test_training_loss_flags_match_the_oracle_masks(predict_mask_token, predict_all):
+    """seq.loss_flags (the host-side integer logic of SSR_Speech.forward, ssr.py:330-345, vectorised) against the oracle's
+    loop restatement — which is pinned to the unmodified reference's loss by tests/test_oracle_golden.py — on random token
+    grids with zero, one and several <mts> occurrences per codebook row, empty / pad / eog tokens mixed in."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    from lm_oracle import LMOracle
+    cfg = cfg_tiny()
+    rng = np.random.default_rng(5)
+    specials = [cfg.empty_token, cfg.eog, cfg.audio_pad_token, cfg.mts, cfg.mts + 1, cfg.mts + 2]
+    for trial in range(40):
+        T = int(rng.integers(2, 40))
+        y = rng.integers(0, cfg.audio_vocab_size, size=(cfg.n_codebooks, T))
+        n_special = int(rng.integers(0, max(1, T // 2)))
+        for _ in range(n_special):
+            y[int(rng.integers(0, cfg.n_codebooks)), int(rng.integers(0, T))] = specials[int(rng.integers(0, len(specials)))]
+        flags = seq.loss_flags(cfg, y, predict_mask_token, predict_all)
+        tg, mask, tmp = LMOracle.loss_masks(cfg, torch.from_numpy(y), predict_mask_token, predict_all)
+        assert flags.dtype == np.uint8 and flags.shape == (cfg.n_codebooks, T - 1)
+        assert np.array_equal(flags & 1, tmp.numpy().astype(np.uint8)), trial
+        assert np.array_equal((flags >> 1) & 1, mask.numpy().astype(np.uint8)), trial
+
+
+@pytest.mark.parametrize("tag", ["default", "all"])
+def test_training_forward_wrapper_combines_like_the_reference(monkeypatch, tag):
+    """SSR_Speech.forward end to end on the CPU with the device call replaced by the oracle: the wrapper's batch handling, loss
+    flags, per-utterance accumulation and the final combination (loss = sum_k mean-CE_k * ntokens_k * weight_k, top-10 accuracy
+    x ntokens; ssr.py:352-372) must reproduce the numbers recorded from the unmodified reference.  (The CUDA kernels behind
+    ssrb_lm_forward_loss are checked against the same golden on the GPU: tests/test_gpu_zzz_train_forward.py.)"""
+    import contextlib
+    import ctypes
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    from lm_oracle import LMOracle
+    from ssr_speech_b200 import _lib, lm as lm_mod
+    from ssr_speech_b200.synth import make_lm_state_dict
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lm_train_forward.npz"))
+    cfg = cfg_tiny()
+    oracle = LMOracle(cfg, make_lm_state_dict(cfg, seed=int(g["weights_seed"])))
+    K, V = cfg.n_codebooks, cfg.n_audio_tokens
+
+    class FakeLib:
+        @staticmethod
+        def ssrb_lm_forward_loss(h, text_p, Lx, audio_p, Ty, flags_p, out_p, stream):
+            text = np.ctypeslib.as_array(ctypes.cast(text_p, ctypes.POINTER(ctypes.c_int32)), (Lx,))
+            audio = np.ctypeslib.as_array(ctypes.cast(audio_p, ctypes.POINTER(ctypes.c_int32)), (K, Ty))
+            flags = np.ctypeslib.as_array(ctypes.cast(flags_p, ctypes.POINTER(ctypes.c_uint8)), (K, Ty - 1))
+            out = np.ctypeslib.as_array(ctypes.cast(out_p, ctypes.POINTER(ctypes.c_double)), (K, 4))
+            logits = oracle.teacher_forced_logits(torch.from_numpy(text.astype(np.int64)), torch.from_numpy(audio.astype(np.int64)))[:-1].double()
+            for k in range(K):
+                sel = torch.from_numpy((flags[k] & 1).astype(bool))
+                tgt = torch.from_numpy(audio[k, 1:].astype(np.int64))
+                lk = logits[:, k][sel]
+                out[k, 0] = float(torch.nn.functional.cross_entropy(lk, tgt[sel], reduction="sum")) if sel.any() else 0.0
+                out[k, 1] = int(sel.sum())
+                out[k, 2] = int((lk.topk(10, dim=-1).indices == tgt[sel][:, None]).any(-1).sum()) if sel.any() else 0
+                out[k, 3] = int(((flags[k] >> 1) & 1).sum())
+            return 0
+
+    ns = cfg.to_namespace()
+    ns.predict_mask_token, ns.predict_all = int(g[f"{tag}_predict_mask_token"]), int(g[f"{tag}_predict_all"])
+    ns.codebook_weight = None if tag == "all" else str(g[f"{tag}_codebook_weight"].tolist())
+    m = lm_mod.SSR_Speech(ns, precision="fp32")
+    m._device = torch.device("cpu")
+    m._h = ctypes.c_void_p(1)
+    monkeypatch.setattr(m, "_ensure_engine", lambda *a, **k: None)
+    monkeypatch.setattr(_lib, "load", lambda: FakeLib)
+    monkeypatch.setattr(_lib, "stream_ptr", lambda: None)
+    monkeypatch.setattr(torch.cuda, "device", lambda d: contextlib.nullcontext())
+    out = m.forward({"x": torch.from_numpy(g["x"]), "x_lens": torch.from_numpy(g["x_lens"]), "y": torch.from_numpy(g["y"]),
+                     "y_lens": torch.from_numpy(g["y_lens"])})
+    m._h = None
+    assert int(out["effective_ntoken"]) == int(g[f"{tag}_ntoken"])
+    assert abs(float(out["loss"]) - float(g[f"{tag}_loss"])) <= 1e-5 * abs(float(g[f"{tag}_loss"]))
+    assert abs(float(out["top10acc"]) - float(g[f"{tag}_top10acc"])) <= 1e-3
+    assert np.allclose([float(v) for v in out["top10acc_by_codebook"]], g[f"{tag}_top10acc_by_codebook"], atol=1e-3)
